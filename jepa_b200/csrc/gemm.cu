@@ -1,0 +1,489 @@
+// tcgen05 GEMM for the V-JEPA hot path (sm_100a only).
+//
+//   D[M,N] = epi( alpha * sum_k A[m,k] * B[n,k] )        bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : MMA issuer     (one thread issues tcgen05.mma, commits free the smem stages)
+//   warps 2..9  : epilogue       (tcgen05.ld -> bias / GELU / residual / dGELU -> smem -> TMA store)
+// The accumulator is double-buffered in TMEM (2 x BN columns) so tile i's epilogue overlaps tile
+// i+1's main loop.  Operands may be K-major (reduction dim contiguous; nn.Linear forward) or
+// MN-major (reduction dim strided; dgrad reads W[N_out,K_in] as B, wgrad reads dY and X
+// transposed) - the smem descriptors change, not the data in HBM, so no transposes are
+// materialised.  Split-K work items reduce into fp32 D with TMA reduce-add.
+//
+// Replaces the cuBLASLt calls behind nn.Linear on the reference path:
+// src/models/utils/modules.py:31-34 (fc1/fc2), :63 (qkv), :76 (proj),
+// src/models/predictor.py:194,237 (predictor_embed / predictor_proj),
+// src/models/utils/patch_embed.py:54-57 (Conv3d as GEMM) and their autograd backward.
+
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "vjepa_b200.h"
+
+namespace vj {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kEpiBufBytes = 4096;
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, split_k, kb_total, kb_per_split;
+  const float* bias;
+  int epi;
+  const void* aux;
+  long long ldaux;
+  int aux_f32;
+  const int* aux_rowmap;
+  int aux_period;
+  int has_auxout;
+  int reduce_add;
+  float alpha;
+  // smem-descriptor strides (bytes); overridable through VJ_DBG_* env vars while bringing the
+  // kernel up on hardware.
+  unsigned lbo_k, sbo_k, lbo_mn, sbo_mn;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFF = EPI_OFF + kEpiWarps * kEpiBufBytes;
+  static constexpr int BAR_OFF = BIAS_OFF + BN * 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+VJ_DEVINL uint32_t swz_off(int row, int chunk, bool rows128) {
+  return rows128 ? uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4))
+                 : uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+VJ_DEVINL void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) - far below the bf16 rounding of the result.
+VJ_DEVINL float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float r = 1.0f - poly * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+VJ_DEVINL float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+VJ_DEVINL float gelu_grad_fast(float x) {
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
+            const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* epi_base = smem + Cfg::EPI_OFF;
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES);
+  const uint32_t tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int total = tiles * p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = w / tiles;
+        const int t = w - split * tiles;
+        const int m0 = (t / p.tiles_n) * BM;
+        const int n0 = (t % p.tiles_n) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, fb, m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, fb, n0 + 64 * j, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int split = w / tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = A_MN ? make_smem_desc(sa + kk * 2048, p.lbo_mn, p.sbo_mn, 2)
+                                     : make_smem_desc(sa + kk * 32, p.lbo_k, p.sbo_k, 2);
+            const uint64_t db = B_MN ? make_smem_desc(sb + kk * 2048, p.lbo_mn, p.sbo_mn, 2)
+                                     : make_smem_desc(sb + kk * 32, p.lbo_k, p.sbo_k, 2);
+            umma_f16(tacc, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);  // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int g = ew >> 2;    // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int NCHUNK = COLS_PER_WARP / 32;
+    uint8_t* buf = epi_base + ew * kEpiBufBytes;
+    const uint32_t buf_u32 = smem_u32(buf);
+    const int etid = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr bool OUT128 = OUT_F32;  // staged rows are 128 B (fp32) or 64 B (bf16)
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int split = w / tiles;
+      const int t = w - split * tiles;
+      const int m0 = (t / p.tiles_n) * BM;
+      const int n0 = (t % p.tiles_n) * BN;
+
+      named_bar_sync(1, kEpiWarps * 32);
+      for (int i = etid; i < BN; i += kEpiWarps * 32)
+        bias_s[i] = (p.bias != nullptr && split == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+      named_bar_sync(1, kEpiWarps * 32);
+
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int row0 = m0 + q * 32;
+
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col0 = g * COLS_PER_WARP + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + col0), v);
+        tmem_wait_ld();
+        if (c == NCHUNK - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, bias_s[col0 + j]);
+
+        // the staging buffer is free again once the previous TMA store has read it
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
+
+        if (p.epi == VJ_EPI_ADD || p.epi == VJ_EPI_DGELU) {
+          // coalesced global -> smem of the aux tile (32 rows x 32 cols), then each thread
+          // picks up its own row.
+          const bool a128 = p.aux_f32 != 0;
+          const int cpr = a128 ? 8 : 4;  // 16B chunks per row
+          const int rows_per_it = 32 / cpr;
+          const int ch = lane % cpr;
+          for (int it = 0; it < cpr; ++it) {
+            const int r = it * rows_per_it + lane / cpr;
+            const int grow = row0 + r;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (grow < p.M) {
+              long long srow = grow;
+              if (p.aux_rowmap != nullptr) srow = p.aux_rowmap[grow];
+              else if (p.aux_period > 0) srow = grow % p.aux_period;
+              const long long ecol = n0 + col0 + ch * (a128 ? 4 : 8);
+              if (ecol < p.N) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) +
+                                     (srow * p.ldaux + ecol) * (a128 ? 4 : 2);
+                val = *reinterpret_cast<const uint4*>(src);
+              }
+            }
+            *reinterpret_cast<uint4*>(buf + swz_off(r, ch, a128)) = val;
+          }
+          __syncwarp();
+          float a[32];
+          if (a128) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(buf + swz_off(lane, j, true));
+              a[4 * j] = x.x; a[4 * j + 1] = x.y; a[4 * j + 2] = x.z; a[4 * j + 3] = x.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 x = *reinterpret_cast<const uint4*>(buf + swz_off(lane, j, false));
+              a[8 * j] = bf16_lo(x.x); a[8 * j + 1] = bf16_hi(x.x);
+              a[8 * j + 2] = bf16_lo(x.y); a[8 * j + 3] = bf16_hi(x.y);
+              a[8 * j + 4] = bf16_lo(x.z); a[8 * j + 5] = bf16_hi(x.z);
+              a[8 * j + 6] = bf16_lo(x.w); a[8 * j + 7] = bf16_hi(x.w);
+            }
+          }
+          __syncwarp();
+          if (p.epi == VJ_EPI_ADD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += a[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= gelu_grad_fast(a[j]);
+          }
+        } else if (p.epi == VJ_EPI_GELU) {
+          if (p.has_auxout) {
+            // pre-activation (needed by the backward) goes out first through the same buffer
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(buf + swz_off(lane, j, false)) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmX, buf_u32, n0 + col0, row0);
+              tma_commit_group();
+              tma_wait_group_read<0>();
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+        }
+
+        if (OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<float4*>(buf + swz_off(lane, j, true)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            *reinterpret_cast<uint4*>(buf + swz_off(lane, j, OUT128)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (OUT_F32 && p.reduce_add) tma_reduce_add_2d(&tmD, buf_u32, n0 + col0, row0);
+          else tma_store_2d(&tmD, buf_u32, n0 + col0, row0);
+          tma_commit_group();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_wait_group<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD,
+                       const CUtensorMap& tX, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.split_k;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tD, tX, p);
+  VJ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(int a_mn, int b_mn, int out_f32, const CUtensorMap& tA,
+                          const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tX,
+                          const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) {
+    return out_f32 ? launch_gemm<BN, false, false, true>(tA, tB, tD, tX, p, s)
+                   : launch_gemm<BN, false, false, false>(tA, tB, tD, tX, p, s);
+  }
+  if (!a_mn && b_mn) {
+    return out_f32 ? launch_gemm<BN, false, true, true>(tA, tB, tD, tX, p, s)
+                   : launch_gemm<BN, false, true, false>(tA, tB, tD, tX, p, s);
+  }
+  if (a_mn && b_mn) {
+    return out_f32 ? launch_gemm<BN, true, true, true>(tA, tB, tD, tX, p, s)
+                   : launch_gemm<BN, true, true, false>(tA, tB, tD, tX, p, s);
+  }
+  set_error("vj_gemm: A MN-major with B K-major is not instantiated");
+  return -1;
+}
+
+}  // namespace vj
+
+extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, long long ldb,
+                       int b_mn, void* D, long long ldd, int d_f32, int M, int N, int K,
+                       const float* bias, float alpha, int epi, const void* aux, long long ldaux,
+                       int aux_f32, const int* aux_rowmap, int aux_period, void* aux_out,
+                       long long ldauxout, int split_k, int accumulate, void* stream_) {
+  using namespace vj;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(A && B && D, "vj_gemm: null operand");
+  VJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "vj_gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VJ_CHECK_ARG(N % 64 == 0, "vj_gemm: N=%d must be a multiple of 64", N);
+  VJ_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "vj_gemm: K/lda/ldb must be multiples of 8");
+  VJ_CHECK_ARG(ldd % (d_f32 ? 4 : 8) == 0, "vj_gemm: ldd misaligned");
+  VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+               "vj_gemm: operands must be 16-byte aligned");
+  VJ_CHECK_ARG(epi >= VJ_EPI_NONE && epi <= VJ_EPI_DGELU, "vj_gemm: bad epilogue %d", epi);
+  VJ_CHECK_ARG(!(accumulate || split_k > 1) || d_f32, "vj_gemm: accumulate/split-K needs fp32 D");
+  if (epi == VJ_EPI_ADD || epi == VJ_EPI_DGELU) {
+    VJ_CHECK_ARG(aux != nullptr, "vj_gemm: epilogue %d needs aux", epi);
+    VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldaux % (aux_f32 ? 4 : 8) == 0,
+                 "vj_gemm: aux misaligned");
+  }
+  if (a_mn) VJ_CHECK_ARG(M % 8 == 0, "vj_gemm: MN-major A needs M %% 8 == 0");
+
+  const int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = N / BN;
+  p.kb_total = (K + BK - 1) / BK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > p.kb_total) split_k = p.kb_total;
+  p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.bias = bias;
+  p.epi = epi;
+  p.aux = aux; p.ldaux = ldaux; p.aux_f32 = aux_f32; p.aux_rowmap = aux_rowmap; p.aux_period = aux_period;
+  p.has_auxout = (epi == VJ_EPI_GELU && aux_out != nullptr) ? 1 : 0;
+  p.reduce_add = (accumulate || p.split_k > 1) ? 1 : 0;
+  p.alpha = alpha;
+  p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;
+  if (const char* e = getenv("VJ_DBG_LBO_K")) p.lbo_k = unsigned(atoi(e));
+  if (const char* e = getenv("VJ_DBG_SBO_K")) p.sbo_k = unsigned(atoi(e));
+  if (const char* e = getenv("VJ_DBG_LBO_MN")) p.lbo_mn = unsigned(atoi(e));
+  if (const char* e = getenv("VJ_DBG_SBO_MN")) p.sbo_mn = unsigned(atoi(e));
+
+  CUtensorMap tA, tB, tD, tX;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d(&tA, A, 0, K, M, lda * 2, 64, 128, 3);
+  else       rc = make_tmap_2d(&tA, A, 0, M, K, lda * 2, 64, 64, 3);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_2d(&tB, B, 0, K, N, ldb * 2, 64, BN, 3);
+  else       rc = make_tmap_2d(&tB, B, 0, N, K, ldb * 2, 64, 64, 3);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tD, D, d_f32 ? 1 : 0, N, M, ldd * (d_f32 ? 4 : 2), 32, 32, d_f32 ? 3 : 2);
+  if (rc) return rc;
+  if (p.has_auxout) {
+    VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(aux_out) & 15) == 0 && ldauxout % 8 == 0, "vj_gemm: aux_out misaligned");
+    rc = make_tmap_2d(&tX, aux_out, 0, N, M, ldauxout * 2, 32, 32, 2);
+    if (rc) return rc;
+  } else {
+    tX = tD;
+  }
+  switch (BN) {
+    case 256: return dispatch_major<256>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
+    default:  return dispatch_major<64>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
+  }
+}
