@@ -48,6 +48,94 @@ int vj_gemm(const void* A, long long lda, int a_mn, const void* B, long long ldb
             int aux_period, void* aux_out, long long ldauxout, int split_k, int accumulate,
             void* stream);
 
+/* Dense var-len flash attention forward (tcgen05).  qkv bf16 [T, 3*H*HD] (q|k|v thirds, head-major),
+ * out bf16 [T, H*HD], lse2 fp32 [H, T] (log2 domain).  Sequences are the row ranges
+ * [cu_seqlens[s], cu_seqlens[s+1]) (device int32 [nseq+1]); max_len = longest sequence.
+ * HD in {32, 64, 128} (hd=24 heads are zero-padded to 32 by the weight layout).
+ * Replaces F.scaled_dot_product_attention, src/models/utils/modules.py:66-69. */
+int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* cu_seqlens, int nseq, int max_len,
+                int H, int HD, int T, float scale, void* stream);
+
+/* Backward of the above: dqkv bf16 [T, 3*H*HD] from dout bf16 [T, H*HD]; delta_ws fp32 [H*T] scratch.
+ * (autograd of modules.py:66-69). */
+int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
+                void* dqkv, const int* cu_seqlens, int nseq, int max_len, int H, int HD, int T, float scale,
+                void* stream);
+
+/* LayerNorm over the last dim, one warp per row.  x bf16|fp32 [T,D] -> y bf16|fp32; mean/rstd fp32 [T]
+ * (nullable) are saved for the backward.  nn.LayerNorm(eps=1e-6) at modules.py:115,119,
+ * vision_transformer.py:192-193, predictor.py:233. */
+int vj_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, const float* gamma, const float* beta,
+                     float* mean, float* rstd, int T, int D, float eps, void* stream);
+size_t vj_layernorm_bwd_workspace(int T, int D);
+/* dx = dres + LN'(dy) (dres nullable, same dtype as x/dx); dgamma/dbeta fp32 [D] are ACCUMULATED (+=). */
+int vj_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean,
+                     const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                     void* workspace, size_t ws_bytes, int T, int D, void* stream);
+
+/* out[N] += column sums of in[T,N] (bf16|fp32) over rows r with lo <= r % period < hi (period<=0: all).
+ * Bias gradients of every nn.Linear; mask-token gradient (predictor.py:207-210 backward). */
+int vj_colsum(const void* in, int in_f32, float* out, long long T, int N, long long ld, int period, int lo,
+              int hi, void* stream);
+
+/* Tubelet im2col: clips fp32 [B,C,T,H,W] -> patches bf16 [B*K', C*tub*ps*ps] in Conv3d weight order
+ * (c,dt,dh,dw); idx (int64 [B,K], nullable) gathers tokens first (context path), else K' = all tokens.
+ * PatchEmbed3D, src/models/utils/patch_embed.py:47-57 (+ apply_masks, vision_transformer.py:178-180). */
+int vj_im2col_tubelets(const float* clips, void* patches, const long long* idx, int B, int C, int T, int H,
+                       int W, int tubelet, int patch, int K, void* stream);
+
+/* out[b,k,:] = x[b, idx[b,k], :], rows of row_bytes (multiple of 16).  apply_masks, src/masks/utils.py:11-23. */
+int vj_gather_rows(const void* x, void* out, const long long* idx, int B, int N, int K, int row_bytes,
+                   void* stream);
+/* dx[b, idx[b,k], :] += dy[b,k,:]  (backward of the gather; indices unique per row). */
+int vj_scatter_rows_add(const void* dy, void* dx, const long long* idx, int B, int N, int K, int D, int f32,
+                        void* stream);
+
+/* Targets: out fp32 [B,K,D] = layer_norm(LN_affine(x[b, idx[b,k]]; eps_norm), eps_target, no affine).
+ * vision_transformer.py:192-193 + app/vjepa/train.py:426-428 fused, gathered rows only. */
+int vj_target_ln_gather(const void* x, float* out, const long long* idx, const float* gamma, const float* beta,
+                        int B, int N, int K, int D, float eps_norm, float eps_target, void* stream);
+
+/* Predictor input for one mask: x[b,:Ke] = emb[b] + pos[idx_ctx[b]]; x[b,Ke:] = mask_token + pos[idx_tgt[b]].
+ * emb bf16 [B*Ke,Dp], pos fp32 [N,Dp], x bf16|fp32 [B,Ke+Kp,Dp].  src/models/predictor.py:194-221. */
+int vj_pred_assemble_fwd(const void* emb, const float* pos, const float* mask_token, const long long* idx_ctx,
+                         const long long* idx_tgt, void* x, int x_f32, int B, int Ke, int Kp, int Dp, void* stream);
+/* demb bf16 [B*Ke,Dp] = dx[:, :Ke];  dmask_token fp32 [Dp] += sum of dx[:, Ke:]. */
+int vj_pred_assemble_bwd(const void* dx, int dx_f32, void* demb, float* dmask_token, int B, int Ke, int Kp,
+                         int Dp, void* stream);
+/* scatter=0: dst[B*Kp,D] = src[B,Ke+Kp,D][:, Ke:]  (predictor.py:236);  scatter=1: the reverse
+ * (zero_ctx: also zero the first Ke rows of every sequence). */
+int vj_seq_slice(const void* src, void* dst, int f32, int B, int Ke, int Kp, int D, int scatter, int zero_ctx,
+                 void* stream);
+
+/* loss_sum[0] += sum |z - h|   (z bf16, h fp32, n elements).  app/vjepa/train.py:440-446. */
+int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, void* stream);
+/* dz bf16 = sign(z - h) * scale * (grad_scale_dev ? *grad_scale_dev : 1). */
+int vj_l1_loss_bwd(const void* z, const float* h, const float* grad_scale_dev, float scale, void* dz,
+                   long long n, void* stream);
+/* pstd[b,d] += weight * sqrt(var_unbiased_k(z[b,k,d]) + eps).  reg_fn, app/vjepa/train.py:448-449. */
+int vj_token_std_accum(const void* z, float* pstd, int B, int K, int D, float eps, float weight, void* stream);
+
+/* ---- flat-buffer parameter kernels ------------------------------------------------------------ */
+/* dst bf16[n] = src fp32[n]: the per-step bf16 shadow of the fp32 master weights (what autocast's
+ * weight cast does for every F.linear under torch.cuda.amp.autocast, app/vjepa/train.py:453). */
+int vj_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* Tensors viewed as [outer, G, hd, inner] <-> [outer, G, hdp, inner]: zero-pad heads (unpad_add=0) or
+ * accumulate the padded fp32 gradient back into the unpadded one (unpad_add=1).  Predictor heads are
+ * hd = 384/16 = 24 (app/vjepa/utils.py:119) and run as 32-wide tcgen05 tiles. */
+int vj_head_pad(const void* src, int src_f32, void* dst, int dst_f32, long long outer, int G, int hd, int hdp,
+                long long inner, int unpad_add, void* stream);
+/* k = k*m + one_minus_m*q over a flat fp32 buffer, rounding op-for-op like
+ * param_k.mul_(m).add_((1.-m)*param_q)  (app/vjepa/train.py:484-487). */
+int vj_ema_update(float* k, const float* q, long long n, float m, float one_minus_m, void* stream);
+/* One AdamW step over a flat fp32 segment (torch.optim.AdamW rule; app/vjepa/utils.py:173-194).
+ * inv_scale_dev / found_inf_dev (device scalars, nullable) implement GradScaler unscale + skip. */
+int vj_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, const float* inv_scale_dev, const float* found_inf_dev,
+                  void* stream);
+/* out[0] += sum(x^2) over a flat fp32 buffer (grad-norm statistics, src/utils/logging.py:91-105). */
+int vj_sumsq(const float* x, long long n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

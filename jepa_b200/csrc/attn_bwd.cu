@@ -1,0 +1,518 @@
+// Flash-attention backward on tcgen05 / TMEM (sm_100a), dense var-len, deterministic (no atomics).
+//
+// Backward of F.scaled_dot_product_attention (src/models/utils/modules.py:66-69):
+//   P = softmax(scale Q K^T), dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)),
+//   dQ = scale dS K, dK = scale dS^T Q.
+// Three kernels:
+//   attn_delta_kernel : delta[h,t] = sum_d dO[t,h,d] O[t,h,d]                      (HBM-bound)
+//   attn_bwd_dkv_kernel: one CTA per 128-key tile, loops over query tiles; computes S^T = K Q^T and
+//                        dP^T = V dO^T directly in the transposed orientation so P^T / dS^T are the
+//                        M-side (K-major) operands of dV += P^T dO and dK += dS^T Q, both accumulated
+//                        in TMEM across the whole loop.
+//   attn_bwd_dq_kernel : one CTA per 128-query tile, loops over key tiles; dQ += dS K in TMEM.
+// P is recomputed from the forward's log2-domain LSE.  Same qkv / O layouts as attn_fwd.cu; the
+// gradient dqkv has the qkv layout [T, 3*H*HD] so the qkv wgrad/dgrad GEMMs consume it directly.
+#include "attn_common.cuh"
+#include "vjepa_b200.h"
+
+namespace vj {
+
+struct AttnBwdParams {
+  const int* cu_seqlens;
+  const float* lse2;
+  const float* delta;
+  __nv_bfloat16* dqkv;
+  int H, T;
+  float scale, scale_log2;
+};
+
+template <int HD>
+struct BwdCfg {
+  using A = AttnCfg<HD>;
+  // four [128 x HD] operand tiles + one [128 x 128] bf16 P/dS tile + stats + barriers
+  static constexpr int T0 = 0, T1 = A::TILE_BYTES, T2 = 2 * A::TILE_BYTES, T3 = 3 * A::TILE_BYTES;
+  static constexpr int PS_OFF = 4 * A::TILE_BYTES;
+  static constexpr int STAT_OFF = PS_OFF + A::P_BYTES;        // [2][2][128] floats
+  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 128 * 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
+  static constexpr int DKV_TMEM = (128 + 2 * HD) <= 256 ? 256 : 512;
+  static constexpr int DQ_TMEM = (128 + HD) <= 256 ? 256 : 512;
+};
+
+VJ_DEVINL void named_bar_sync_attn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// write 8 packed bf16 (16 bytes) of row r, 16-byte column chunk col8 (0..15) into a [128x128] K-major tile
+VJ_DEVINL void ptile_store(uint8_t* tile, int r, int col8, const uint4& u) {
+  *reinterpret_cast<uint4*>(tile + (col8 >> 3) * 16384 + r * 128 + (((col8 & 7) ^ (r & 7)) << 4)) = u;
+}
+
+// coalesced store of a per-warp staged [32 rows x HD] bf16 block to global rows
+template <int HD>
+VJ_DEVINL void store_rows_bf16(uint8_t* stage, const float (&vals)[HD], float mul, int lane, __nv_bfloat16* gbase,
+                               long long ld, int row_first, int rows_valid) {
+  constexpr int ORB = HD * 2, CH = ORB / 16, ROWS_PER_IT = 32 / CH;
+#pragma unroll
+  for (int g = 0; g < CH; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(vals[8 * g + 0] * mul, vals[8 * g + 1] * mul);
+    u.y = pack_bf16x2(vals[8 * g + 2] * mul, vals[8 * g + 3] * mul);
+    u.z = pack_bf16x2(vals[8 * g + 4] * mul, vals[8 * g + 5] * mul);
+    u.w = pack_bf16x2(vals[8 * g + 6] * mul, vals[8 * g + 7] * mul);
+    *reinterpret_cast<uint4*>(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4)) = u;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < CH; ++it) {
+    const int rr = it * ROWS_PER_IT + lane / CH;
+    const int g = lane % CH;
+    if (rr < rows_valid) {
+      const uint4 u = *reinterpret_cast<const uint4*>(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase) + ((long long)(row_first + rr) * ld) * 2 + g * 16) = u;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// delta[h, t] = sum_d dO[t, h*HD + d] * O[t, h*HD + d]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ dout,
+                                                         float* __restrict__ delta, int T, int H, int HD) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int D = H * HD;
+  const int nvec = D >> 3;
+  const int lanes_per_head = HD >> 3;
+  for (long long t = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); t < T; t += (long long)gridDim.x * wpb) {
+    for (int c = lane; c < ((nvec + 31) / 32) * 32; c += 32) {
+      float s = 0.f;
+      if (c < nvec) {
+        const uint4 a = *reinterpret_cast<const uint4*>(o + t * D + c * 8);
+        const uint4 b = *reinterpret_cast<const uint4*>(dout + t * D + c * 8);
+        s = bf16_lo(a.x) * bf16_lo(b.x) + bf16_hi(a.x) * bf16_hi(b.x) + bf16_lo(a.y) * bf16_lo(b.y) +
+            bf16_hi(a.y) * bf16_hi(b.y) + bf16_lo(a.z) * bf16_lo(b.z) + bf16_hi(a.z) * bf16_hi(b.z) +
+            bf16_lo(a.w) * bf16_lo(b.w) + bf16_hi(a.w) * bf16_hi(b.w);
+      }
+      for (int o2 = lanes_per_head >> 1; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+      if (c < nvec && (lane % lanes_per_head) == 0) delta[(long long)((c * 8) / HD) * T + t] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dK / dV : CTA = (kv tile, sequence, head)
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdParams p) {
+  using C = AttnCfg<HD>;
+  using B = BwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int seq = blockIdx.y, head = blockIdx.z;
+  const int row_begin = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - row_begin;
+  const int kv0 = blockIdx.x * 128;
+  if (kv0 >= len) return;
+  const int n_q = (len + 127) / 128;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B::BAR_OFF);
+  const uint32_t bar_kv = smem_u32(bars + 0), bar_qdo = smem_u32(bars + 1), bar_qdofree = smem_u32(bars + 2);
+  const uint32_t bar_s = smem_u32(bars + 3), bar_p = smem_u32(bars + 4), bar_pvdone = smem_u32(bars + 5);
+  const uint32_t bar_dp = smem_u32(bars + 6), bar_ds = smem_u32(bars + 7);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_qdo, 1); mbar_init(bar_qdofree, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); }
+  if (warp == 1) tmem_alloc<B::DKV_TMEM>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_ST = tmem_base, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 128 + HD;
+  const uint32_t sK = smem_u32(smem + B::T0), sV = smem_u32(smem + B::T1);
+  const uint32_t sQ = smem_u32(smem + B::T2), sDO = smem_u32(smem + B::T3), sPS = smem_u32(smem + B::PS_OFF);
+  const int HHD = p.H * HD;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_kv, 2 * C::TILE_BYTES);
+#pragma unroll
+      for (int b = 0; b < C::NBOX; ++b) {
+        tma_load_2d(sK + b * C::BOX_BYTES, &tmQKV, bar_kv, HHD + head * HD + b * C::BOX_INNER, row_begin + kv0);
+        tma_load_2d(sV + b * C::BOX_BYTES, &tmQKV, bar_kv, 2 * HHD + head * HD + b * C::BOX_INNER, row_begin + kv0);
+      }
+      for (int i = 0; i < n_q; ++i) {
+        mbar_wait(bar_qdofree, (i & 1) ^ 1);
+        mbar_expect_tx(bar_qdo, 2 * C::TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < C::NBOX; ++b) {
+          tma_load_2d(sQ + b * C::BOX_BYTES, &tmQKV, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + i * 128);
+          tma_load_2d(sDO + b * C::BOX_BYTES, &tmDO, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + i * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_128 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_hd = make_idesc_bf16(128, HD, 0, 1);
+      mbar_wait(bar_kv, 0);
+      for (int i = 0; i < n_q; ++i) {
+        const uint32_t ph = i & 1;
+        mbar_wait(bar_qdo, ph);
+        tc_fence_after();
+        // S^T = K Q_i^T
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16(tmem_ST, kmajor_desc<HD>(sK, kk), kmajor_desc<HD>(sQ, kk), idesc_128, kk > 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_p, ph);
+        tc_fence_after();
+        // dV += P^T dO_i
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDO, kk), idesc_hd, (i > 0 || kk > 0));
+        umma_commit(bar_pvdone);
+        // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDO, kk), idesc_128, kk > 0);
+        umma_commit(bar_dp);
+        mbar_wait(bar_ds, ph);
+        tc_fence_after();
+        // dK += dS^T Q_i
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQ, kk), idesc_hd, (i > 0 || kk > 0));
+        umma_commit(bar_qdofree);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // key row inside the tile
+    const int tid = threadIdx.x - 64;
+    const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    float* stats = reinterpret_cast<float*>(smem + B::STAT_OFF);
+    uint8_t* ps = smem + B::PS_OFF;
+    for (int i = 0; i < n_q; ++i) {
+      const uint32_t ph = i & 1;
+      float* lse_s = stats + (i & 1) * 256;
+      float* del_s = lse_s + 128;
+      {
+        const int qrow = i * 128 + tid;
+        const bool ok = qrow < len;
+        lse_s[tid] = ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : 0.f;
+        del_s[tid] = ok ? p.delta[(long long)head * p.T + row_begin + qrow] : 0.f;
+      }
+      named_bar_sync_attn(1, 128);
+      const int qvalid = min(128, len - i * 128);
+      // the P/dS tile is free once the previous iteration's dK MMA retired
+      if (i > 0) mbar_wait(bar_qdofree, (i - 1) & 1);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_ST + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int q0i = c * 32 + e;
+          float a = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_s[q0i]));
+          float b = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_s[q0i + 1]));
+          a = q0i < qvalid ? a : 0.f;
+          b = q0i + 1 < qvalid ? b : 0.f;
+          pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          ptile_store(ps, r, c * 4 + g,
+                      make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]));
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(bar_p);
+      mbar_wait(bar_dp, ph);
+      mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_ST + lane_addr + c * 32, v);
+        tmem_wait_ld();
+        uint32_t ds[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int q0i = c * 32 + e;
+          const uint32_t pp = pk[c * 16 + e / 2];
+          const float a = bf16_lo(pp) * (__uint_as_float(v[e]) - del_s[q0i]);
+          const float b = bf16_hi(pp) * (__uint_as_float(v[e + 1]) - del_s[q0i + 1]);
+          ds[e / 2] = pack_bf16x2(a, b);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          ptile_store(ps, r, c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(bar_ds);
+    }
+    // epilogue: dV, dK (x scale) -> bf16 -> dqkv[:, v / k third]
+    mbar_wait(bar_qdofree, (n_q - 1) & 1);
+    tc_fence_after();
+    const int rows_valid = max(0, min(32, len - kv0 - qd * 32));
+    uint8_t* stage = ps + (warp - 2) * (32 * HD * 2);
+    float acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_dV + lane_addr + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[c * 32 + e] = __uint_as_float(v[e]);
+    }
+    store_rows_bf16<HD>(stage, acc, 1.0f, lane, p.dqkv + 2 * HHD + head * HD, 3LL * HHD,
+                        row_begin + kv0 + qd * 32, rows_valid);
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_dK + lane_addr + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[c * 32 + e] = __uint_as_float(v[e]);
+    }
+    store_rows_bf16<HD>(stage, acc, p.scale, lane, p.dqkv + HHD + head * HD, 3LL * HHD,
+                        row_begin + kv0 + qd * 32, rows_valid);
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<B::DKV_TMEM>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dQ : CTA = (query tile, sequence, head)
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnBwdParams p) {
+  using C = AttnCfg<HD>;
+  using B = BwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int seq = blockIdx.y, head = blockIdx.z;
+  const int row_begin = p.cu_seqlens[seq];
+  const int len = p.cu_seqlens[seq + 1] - row_begin;
+  const int q0 = blockIdx.x * 128;
+  if (q0 >= len) return;
+  const int n_kv = (len + 127) / 128;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B::BAR_OFF);
+  const uint32_t bar_qdo = smem_u32(bars + 0), bar_kv = smem_u32(bars + 1), bar_kvfree = smem_u32(bars + 2);
+  const uint32_t bar_s = smem_u32(bars + 3), bar_sread = smem_u32(bars + 4), bar_dp = smem_u32(bars + 5);
+  const uint32_t bar_ds = smem_u32(bars + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_kvfree, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_sread, 128); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); }
+  if (warp == 1) tmem_alloc<B::DQ_TMEM>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dQ = tmem_base + 128;
+  const uint32_t sQ = smem_u32(smem + B::T0), sDO = smem_u32(smem + B::T1);
+  const uint32_t sK = smem_u32(smem + B::T2), sV = smem_u32(smem + B::T3), sDS = smem_u32(smem + B::PS_OFF);
+  const int HHD = p.H * HD;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_qdo, 2 * C::TILE_BYTES);
+#pragma unroll
+      for (int b = 0; b < C::NBOX; ++b) {
+        tma_load_2d(sQ + b * C::BOX_BYTES, &tmQKV, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + q0);
+        tma_load_2d(sDO + b * C::BOX_BYTES, &tmDO, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + q0);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(bar_kvfree, (j & 1) ^ 1);
+        mbar_expect_tx(bar_kv, 2 * C::TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < C::NBOX; ++b) {
+          tma_load_2d(sK + b * C::BOX_BYTES, &tmQKV, bar_kv, HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
+          tma_load_2d(sV + b * C::BOX_BYTES, &tmQKV, bar_kv, 2 * HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_128 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_hd = make_idesc_bf16(128, HD, 0, 1);
+      mbar_wait(bar_qdo, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(bar_kv, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16(tmem_S, kmajor_desc<HD>(sQ, kk), kmajor_desc<HD>(sK, kk), idesc_128, kk > 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_sread, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_f16(tmem_S, kmajor_desc<HD>(sDO, kk), kmajor_desc<HD>(sV, kk), idesc_128, kk > 0);
+        umma_commit(bar_dp);
+        mbar_wait(bar_ds, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_dQ, ptile_desc(sDS, kk), mnmajor_desc<HD>(sK, kk), idesc_hd, (j > 0 || kk > 0));
+        umma_commit(bar_kvfree);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    uint8_t* dsb = smem + B::PS_OFF;
+    const bool row_ok = q0 + r < len;
+    const float lse_r = row_ok ? p.lse2[(long long)head * p.T + row_begin + q0 + r] : 0.f;
+    const float del_r = row_ok ? p.delta[(long long)head * p.T + row_begin + q0 + r] : 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int valid = min(128, len - j * 128);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const int k0i = c * 32 + e;
+          float a = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_r));
+          float b = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_r));
+          a = (row_ok && k0i < valid) ? a : 0.f;
+          b = (row_ok && k0i + 1 < valid) ? b : 0.f;
+          pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_sread);
+      mbar_wait(bar_dp, ph);
+      if (j > 0) mbar_wait(bar_kvfree, (j - 1) & 1);  // previous dQ MMA done reading the dS tile
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_addr + c * 32, v);
+        tmem_wait_ld();
+        uint32_t ds[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const uint32_t pp = pk[c * 16 + e / 2];
+          const float a = bf16_lo(pp) * (__uint_as_float(v[e]) - del_r);
+          const float b = bf16_hi(pp) * (__uint_as_float(v[e + 1]) - del_r);
+          ds[e / 2] = pack_bf16x2(a, b);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          ptile_store(dsb, r, c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(bar_ds);
+    }
+    mbar_wait(bar_kvfree, (n_kv - 1) & 1);
+    tc_fence_after();
+    float acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_dQ + lane_addr + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[c * 32 + e] = __uint_as_float(v[e]);
+    }
+    const int rows_valid = max(0, min(32, len - q0 - qd * 32));
+    store_rows_bf16<HD>(dsb + (warp - 2) * (32 * HD * 2), acc, p.scale, lane, p.dqkv + head * HD, 3LL * HHD,
+                        row_begin + q0 + qd * 32, rows_valid);
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<B::DQ_TMEM>(tmem_base);
+}
+
+template <int HD>
+static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
+                           void* dqkv, const int* cu, int nseq, int max_len, int H, int T, float scale,
+                           cudaStream_t s) {
+  using C = AttnCfg<HD>;
+  using B = BwdCfg<HD>;
+  CUtensorMap tq, tdo;
+  int rc = make_tmap_2d(&tq, qkv, 0, (uint64_t)3 * H * HD, T, (uint64_t)3 * H * HD * 2, C::BOX_INNER, 128, C::TMAP_SWIZZLE);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tdo, dout, 0, (uint64_t)H * HD, T, (uint64_t)H * HD * 2, C::BOX_INNER, 128, C::TMAP_SWIZZLE);
+  if (rc) return rc;
+  auto kdkv = attn_bwd_dkv_kernel<HD>;
+  auto kdq = attn_bwd_dq_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    VJ_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
+    VJ_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
+    configured = true;
+  }
+  {
+    int g = (T + 7) / 8;
+    const int cap = num_sms() * 8;
+    if (g > cap) g = cap;
+    attn_delta_kernel<<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                        reinterpret_cast<const __nv_bfloat16*>(dout), delta, T, H, HD);
+    VJ_CUDA(cudaGetLastError());
+  }
+  AttnBwdParams p;
+  p.cu_seqlens = cu; p.lse2 = lse2; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.H = H; p.T = T; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((max_len + 127) / 128, nseq, H);
+  kdkv<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
+  VJ_CUDA(cudaGetLastError());
+  kdq<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
+  VJ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vj
+
+extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
+                           void* dqkv, const int* cu_seqlens, int nseq, int max_len, int H, int HD, int T, float scale,
+                           void* stream_) {
+  using namespace vj;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(qkv && out && dout && lse2 && delta_ws && dqkv && cu_seqlens, "vj_attn_bwd: null pointer");
+  VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_bwd: empty problem");
+  switch (HD) {
+    case 32: return launch_attn_bwd<32>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
+    case 64: return launch_attn_bwd<64>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
+    case 128: return launch_attn_bwd<128>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
+    default: set_error("vj_attn_bwd: head dim %d unsupported (32/64/128)", HD); return -1;
+  }
+}
