@@ -31,6 +31,8 @@ extern "C" {
 
 const char* vj_last_error_string(void);
 int vj_version(void);
+/* Number of kernels this library has launched so far in this process (monotonic). */
+long long vj_launch_count(void);
 
 /* D[M,N] = epi(alpha * A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulate (tcgen05 / TMEM).
  * a_mn = 0: A stored [M,K] (K contiguous, ld = lda);  a_mn = 1: A stored [K,M] (M contiguous).
@@ -108,8 +110,9 @@ int vj_pred_assemble_bwd(const void* dx, int dx_f32, void* demb, float* dmask_to
 int vj_seq_slice(const void* src, void* dst, int f32, int B, int Ke, int Kp, int D, int scatter, int zero_ctx,
                  void* stream);
 
-/* loss_sum[0] += sum |z - h|   (z bf16, h fp32, n elements).  app/vjepa/train.py:440-446. */
-int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, void* stream);
+/* loss_sum[0] += weight * sum |z - h|   (z bf16, h fp32, n elements; weight = 1/(M*n) gives the
+ * per-mask mean averaged over M masks).  app/vjepa/train.py:440-446. */
+int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, float weight, void* stream);
 /* dz bf16 = sign(z - h) * scale * (grad_scale_dev ? *grad_scale_dev : 1). */
 int vj_l1_loss_bwd(const void* z, const float* h, const float* grad_scale_dev, float scale, void* dz,
                    long long n, void* stream);

@@ -15,6 +15,7 @@ P, I, L, F, Z = c_void_p, c_int, c_longlong, c_float, c_size_t
 SIGNATURES = {
     "vj_last_error_string": (c_char_p, []),
     "vj_version": (I, []),
+    "vj_launch_count": (L, []),
     "vj_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, I, P, F, I, P, L, I, P, I, P, L, I, I, P]),
     "vj_attn_fwd": (I, [P, P, P, P, I, I, I, I, I, F, P]),
     "vj_attn_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, F, P]),
@@ -29,7 +30,7 @@ SIGNATURES = {
     "vj_pred_assemble_fwd": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "vj_pred_assemble_bwd": (I, [P, I, P, P, I, I, I, I, P]),
     "vj_seq_slice": (I, [P, P, I, I, I, I, I, I, I, P]),
-    "vj_l1_loss_fwd": (I, [P, P, P, L, P]),
+    "vj_l1_loss_fwd": (I, [P, P, P, L, F, P]),
     "vj_l1_loss_bwd": (I, [P, P, P, F, P, L, P]),
     "vj_token_std_accum": (I, [P, P, I, I, I, F, F, P]),
     "vj_cast_f32_bf16": (I, [P, P, L, P]),

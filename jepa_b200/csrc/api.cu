@@ -1,6 +1,8 @@
 // Library-level plumbing of the C ABI: thread-local error string, SM count cache and the
 // CUtensorMap encoder (driver entry point resolved lazily so the .so loads without libcuda).
 #include <cudaTypedefs.h>
+
+#include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -11,6 +13,9 @@
 namespace vj {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -80,3 +85,4 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, u
 
 extern "C" const char* vj_last_error_string(void) { return vj::g_err; }
 extern "C" int vj_version(void) { return VJ_VERSION; }
+extern "C" long long vj_launch_count(void) { return vj::g_launches.load(std::memory_order_relaxed); }

@@ -488,6 +488,7 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
     attn_delta_kernel<<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
                                         reinterpret_cast<const __nv_bfloat16*>(dout), delta, T, H, HD);
     VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   }
   AttnBwdParams p;
   p.cu_seqlens = cu; p.lse2 = lse2; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
@@ -495,8 +496,10 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   dim3 grid((max_len + 127) / 128, nseq, H);
   kdkv<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   kdq<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 

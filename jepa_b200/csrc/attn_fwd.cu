@@ -246,6 +246,7 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   dim3 grid((max_len + 127) / 128, nseq, H);
   kern<<<grid, kAttnThreads, C::SMEM_BYTES, s>>>(tm, p);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 

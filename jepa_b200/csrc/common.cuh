@@ -36,6 +36,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+void count_launch(int n);  // bookkeeping for vj_launch_count()
 
 // Encode a 2-D tiled tensor map.  `inner`/`outer` are element counts, `ld_bytes` the byte
 // stride of the outer dimension.  swizzle: 0 none, 1 32B, 2 64B, 3 128B.

@@ -393,6 +393,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tD, tX, p);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 

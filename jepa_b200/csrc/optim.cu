@@ -131,6 +131,7 @@ extern "C" int vj_cast_f32_bf16(const float* src, void* dst, long long n, void* 
   cast_f32_bf16_kernel<<<flat_grid(n / 4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(src),
                                                               reinterpret_cast<uint2*>(dst), n / 4);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -157,6 +158,7 @@ extern "C" int vj_head_pad(const void* src, int src_f32, void* dst, int dst_f32,
     }
   }
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -169,6 +171,7 @@ extern "C" int vj_ema_update(float* k, const float* q, long long n, float m, flo
   ema_kernel<<<flat_grid(n / 4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(k), reinterpret_cast<const float4*>(q), n / 4,
                                                     m, one_minus_m);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -188,6 +191,7 @@ extern "C" int vj_adamw_step(float* p, const float* g, float* m, float* v, long 
                                                       beta1, beta2, eps, weight_decay, float(bc1), float(sqrt(bc2)),
                                                       inv_scale_dev, found_inf_dev);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -198,5 +202,6 @@ extern "C" int vj_sumsq(const float* x, long long n, float* out, void* stream_) 
   if (n <= 0) return 0;
   sumsq_kernel<<<flat_grid(n / 4, 256 * 4), 256, 0, s>>>(reinterpret_cast<const float4*>(x), n / 4, out);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }

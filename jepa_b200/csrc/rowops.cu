@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) seq_slice_kernel(const void* __restrict__
 // =============================================================================================
 __global__ void __launch_bounds__(256) l1_loss_fwd_kernel(const __nv_bfloat16* __restrict__ z,
                                                           const float* __restrict__ h, float* __restrict__ loss_sum,
-                                                          long long n8) {
+                                                          long long n8, float weight) {
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) l1_loss_fwd_kernel(const __nv_bfloat16* _
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += sm[w];
-    atomicAdd(loss_sum, s);
+    atomicAdd(loss_sum, s * weight);
   }
 }
 __global__ void __launch_bounds__(256) l1_loss_bwd_kernel(const __nv_bfloat16* __restrict__ z,
@@ -560,6 +560,7 @@ extern "C" int vj_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, co
   else if (y_f32) ln_fwd_kernel<false, true><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
   else ln_fwd_kernel<false, false><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -588,9 +589,11 @@ extern "C" int vj_layernorm_bwd(const void* dy, const void* x, int x_f32, const 
     ln_bwd_kernel<false><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres,
                                                  dx, pg, pb, T, D);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   colsum_f32_kernel<<<(D + 127) / 128, 128, 0, s>>>(pg, dgamma, grid, D);
   colsum_f32_kernel<<<(D + 127) / 128, 128, 0, s>>>(pb, dbeta, grid, D);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(2);
   return 0;
 }
 
@@ -610,6 +613,7 @@ extern "C" int vj_colsum(const void* in, int in_f32, float* out, long long T, in
   if (in_f32) colsum_kernel<true><<<grid, 256, 0, s>>>(in, out, T, N, ld, int(rpb), period, lo, hi);
   else colsum_kernel<false><<<grid, 256, 0, s>>>(in, out, T, N, ld, int(rpb), period, lo, hi);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -626,6 +630,7 @@ extern "C" int vj_im2col_tubelets(const float* clips, void* patches, const long 
   im2col_kernel<<<grid_for(warps, 8), 256, 0, s>>>(clips, reinterpret_cast<__nv_bfloat16*>(patches), idx, B, C, T, H,
                                                    W, tubelet, patch, kout, n_tokens);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -639,6 +644,7 @@ extern "C" int vj_gather_rows(const void* x, void* out, const long long* idx, in
   gather_rows_kernel<<<grid_for((long long)B * K * vpr, 256), 256, 0, s>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), idx, B, N, K, vpr);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -652,6 +658,7 @@ extern "C" int vj_scatter_rows_add(const void* dy, void* dx, const long long* id
   if (f32) scatter_rows_add_kernel<true><<<g, 256, 0, s>>>(dy, dx, idx, B, N, K, D);
   else scatter_rows_add_kernel<false><<<g, 256, 0, s>>>(dy, dx, idx, B, N, K, D);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -665,6 +672,7 @@ extern "C" int vj_target_ln_gather(const void* x, float* out, const long long* i
   target_ln_gather_kernel<<<grid_for((long long)B * K, 8), 256, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), out, idx, gamma, beta, B, N, K, D, eps_norm, eps_target);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -683,6 +691,7 @@ extern "C" int vj_pred_assemble_fwd(const void* emb, const float* pos, const flo
     pred_assemble_kernel<false><<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(emb), pos, mask_token, idx_ctx,
                                                   idx_tgt, x, B, Ke, Kp, Dp);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -698,6 +707,7 @@ extern "C" int vj_pred_assemble_bwd(const void* dx, int dx_f32, void* demb, floa
   else
     pred_split_ctx_kernel<false><<<g, 256, 0, s>>>(dx, reinterpret_cast<__nv_bfloat16*>(demb), B, Ke, Kp, Dp);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   // mask-token gradient = column sum over the target rows of every sequence
   return vj_colsum(dx, dx_f32, dmask_token, (long long)B * (Ke + Kp), Dp, Dp, Ke + Kp, Ke, Ke + Kp, stream_);
 }
@@ -713,17 +723,20 @@ extern "C" int vj_seq_slice(const void* src, void* dst, int f32, int B, int Ke, 
   if (f32) seq_slice_kernel<true><<<g, 256, 0, s>>>(src, dst, B, Ke, Kp, D, scatter, zero_ctx);
   else seq_slice_kernel<false><<<g, 256, 0, s>>>(src, dst, B, Ke, Kp, D, scatter, zero_ctx);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
-extern "C" int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, void* stream_) {
+extern "C" int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, float weight,
+                              void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   VJ_CHECK_ARG(z && h && loss_sum, "vj_l1_loss_fwd: null pointer");
   VJ_CHECK_ARG(n % 8 == 0, "vj_l1_loss_fwd: n must be a multiple of 8");
   if (n <= 0) return 0;
   l1_loss_fwd_kernel<<<grid_for(n / 8, 256 * 4), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), h, loss_sum,
-                                                              n / 8);
+                                                              n / 8, weight);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -737,6 +750,7 @@ extern "C" int vj_l1_loss_bwd(const void* z, const float* h, const float* grad_s
                                                               grad_scale_dev, scale,
                                                               reinterpret_cast<__nv_bfloat16*>(dz), n / 8);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }
 
@@ -749,5 +763,6 @@ extern "C" int vj_token_std_accum(const void* z, float* pstd, int B, int K, int 
   dim3 grid((D + 127) / 128, B);
   token_std_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), pstd, B, K, D, eps, weight);
   VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
   return 0;
 }

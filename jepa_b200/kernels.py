@@ -176,9 +176,9 @@ def seq_slice(src, dst, B, Ke, Kp, D, scatter=False, zero_ctx=False):
     return dst
 
 
-def l1_loss_fwd(z, h, loss_sum):
+def l1_loss_fwd(z, h, loss_sum, weight):
     _chk(z, BF16, "z"); _chk(h, F32, "h"); _chk(loss_sum, F32, "loss_sum")
-    _lib.call("vj_l1_loss_fwd", _p(z), _p(h), _p(loss_sum), z.numel(), _s())
+    _lib.call("vj_l1_loss_fwd", _p(z), _p(h), _p(loss_sum), z.numel(), float(weight), _s())
 
 
 def l1_loss_bwd(z, h, grad_scale, scale, dz):

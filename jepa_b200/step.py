@@ -1,0 +1,110 @@
+"""The V-JEPA train-step pieces that live as closures inside app/vjepa/train.py:414-498 in the
+reference: target forward (+ LN + gather), L1 latent loss, variance regulariser, EMA update.
+Each is a thin host wrapper over fused kernels; `app/vjepa/train.py` and `bench.py` both call these.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import engine
+from . import kernels as K
+from .models import _common_base, _token_views, MultiMaskWrapper, PredictorMultiMaskWrapper
+
+TARGET_LN_EPS = 1e-5  # F.layer_norm default eps, app/vjepa/train.py:426
+
+
+def unwrap(module):
+    """Strip DistributedDataParallel / multi-mask wrappers down to the backbone."""
+    m = module
+    if hasattr(m, "module") and isinstance(m, torch.nn.parallel.DistributedDataParallel):
+        m = m.module
+    if isinstance(m, (MultiMaskWrapper, PredictorMultiMaskWrapper)):
+        m = m.backbone
+    return m
+
+
+@torch.no_grad()
+def forward_target(target_encoder, clips, masks_pred):
+    """forward_target (train.py:419-429): h = LN_noaffine(target_encoder(clips)) gathered at masks_pred.
+
+    Runs the no-grad encoder over all N tokens, then ONE fused kernel per mask applies the final
+    encoder LayerNorm, the affine-free F.layer_norm and the gather, touching only the kept rows.
+    Returns a list of fp32 [B, Kp_i, D] views of one contiguous buffer.
+    """
+    bb = unwrap(target_encoder)
+    x = bb._check_input(clips)
+    raw, _, _ = engine.encoder_forward(bb, x, None, save=False, final_norm=False)
+    B, N, D = x.shape[0], bb.num_patches, bb.embed_dim
+    raw = raw.view(B, N, D)
+    store = bb._store
+    sizes = [int(m.shape[1]) for m in masks_pred]
+    h_cat = torch.empty(sum(B * k for k in sizes), D, dtype=torch.float32, device=clips.device)
+    off = 0
+    for m, k in zip(masks_pred, sizes):
+        K.target_ln_gather(raw, m.contiguous(), store.f32("norm.weight"), store.f32("norm.bias"), engine.LN_EPS,
+                           TARGET_LN_EPS, out=h_cat[off:off + B * k].view(B, k, D))
+        off += B * k
+    return _token_views(h_cat, B, sizes)
+
+
+class _L1LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_cat, h_cat, row_counts):
+        n_masks = len(row_counts)
+        D = z_cat.shape[1]
+        loss = torch.zeros(1, dtype=torch.float32, device=z_cat.device)
+        off = 0
+        for rows in row_counts:
+            K.l1_loss_fwd(z_cat[off:off + rows], h_cat[off:off + rows], loss, 1.0 / (n_masks * rows * D))
+            off += rows
+        ctx.save_for_backward(z_cat, h_cat)
+        ctx.row_counts = row_counts
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        z_cat, h_cat = ctx.saved_tensors
+        n_masks = len(ctx.row_counts)
+        D = z_cat.shape[1]
+        g = g.detach().to(torch.float32).contiguous()
+        dz = torch.empty_like(z_cat)
+        off = 0
+        for rows in ctx.row_counts:
+            K.l1_loss_bwd(z_cat[off:off + rows], h_cat[off:off + rows], g, 1.0 / (n_masks * rows * D),
+                          dz[off:off + rows])
+            off += rows
+        return dz, None, None
+
+
+def jepa_loss(z, h, loss_exp=1.0):
+    """loss_fn (train.py:440-446): (1/M) sum_i mean(|z_i - h_i|^p) / p, fused for p = 1."""
+    if loss_exp != 1.0:
+        raise NotImplementedError("only loss_exp=1.0 (L1, every shipped config) is implemented on the accelerated path")
+    zb, hb = _common_base(z), _common_base(h)
+    if zb is None:
+        zb = torch.cat([t.reshape(-1, t.shape[-1]) for t in z], dim=0)
+    if hb is None:
+        hb = torch.cat([t.reshape(-1, t.shape[-1]) for t in h], dim=0)
+    if zb.dtype != torch.bfloat16:
+        zb = zb.to(torch.bfloat16)
+    rows = tuple(int(t.shape[0] * t.shape[1]) for t in z)
+    return _L1LossFn.apply(zb.contiguous(), hb.float().contiguous(), rows)
+
+
+@torch.no_grad()
+def reg_loss(z):
+    """reg_fn + relu-mean (train.py:448-449,458-459); value is only logged (reg_coeff = 0 in all configs)."""
+    B, _, D = z[0].shape
+    pstd = torch.zeros(B, D, dtype=torch.float32, device=z[0].device)
+    for zi in z:
+        K.token_std_accum(zi.detach().contiguous(), pstd, 1.0 / len(z))
+    return torch.mean(F.relu(1. - pstd))
+
+
+@torch.no_grad()
+def ema_update(encoder, target_encoder, m):
+    """Momentum update (train.py:484-487) as ONE kernel over the flat parameter buffers."""
+    q, k = unwrap(encoder), unwrap(target_encoder)
+    qs, ks = q._store.adopt(q), k._store.adopt(k)
+    if qs.offsets != ks.offsets:
+        raise RuntimeError("encoder / target_encoder parameter layouts differ")
+    K.ema_update(ks.flat, qs.flat, m)

@@ -1,0 +1,386 @@
+"""GPU parity tests (-m gpu): the CUDA product path, called through the C ABI, against the CPU oracle on
+identical seeded inputs; against the committed reference-generated golden fixtures; and, at full
+BASELINE sizes, through size-independent properties.
+
+Stated tolerances (bf16 operands / fp32 accumulation vs the fp32 oracle):
+  single kernel outputs stored as bf16 : |err| <= 2e-2 + 1e-2 |ref|      (one bf16 rounding + accumulation order)
+  fp32-output kernels (LN stats, loss, wgrad, EMA, AdamW) : rel 1e-4 .. bit-exact where stated
+  whole-network activations rel-L2 <= 3e-2, per-parameter gradients rel-L2 <= 6e-2, loss abs 5e-3
+  index / gather paths: bit-exact (torch.equal)
+"""
+import math
+import os
+import subprocess
+
+import pytest
+import torch
+
+from common import C1, synth_clips
+from parity_util import (TOL_ACT, c1_masks, compare_step, rel_l2, run_c1_step_cuda, run_c1_step_oracle)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    from jepa_b200 import _lib
+    _lib.load()  # fail loudly if the extension is missing - there is no fallback
+    return torch.device("cuda:0")
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def close_bf16(got, ref, atol=2e-2, rtol=1e-2):
+    err = (got.float().cpu() - ref.float()).abs()
+    bound = atol + rtol * ref.float().abs()
+    assert bool((err <= bound).all()), f"max err {float(err.max()):.4g}, worst excess {float((err - bound).max()):.4g}"
+
+
+# --------------------------------------------------------------------------------------------- native
+@pytest.mark.parametrize("binary", ["test_gemm", "test_attn"])
+def test_native_bringup_binaries(dev, binary):
+    exe = os.path.join(ROOT, "tests", "native", binary)
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ALL PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-1000:]
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(200, 192, 192), (333, 384, 1536), (1000, 1024, 256)])
+def test_linear_forward_epilogues(dev, M, N, K):
+    from jepa_b200 import kernels as Kn
+    from oracle import vjepa_oracle as O
+    g = torch.Generator().manual_seed(M + N)
+    x, w = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    b = torch.randn(N, generator=g) * 0.1
+    res = bf(torch.randn(M, N, generator=g))
+    xd, wd, bd, resd = x.to(dev, torch.bfloat16), w.to(dev, torch.bfloat16), b.to(dev), res.to(dev, torch.bfloat16)
+    ref = O.linear(x, w, b)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    close_bf16(Kn.gemm(xd, wd, out, bias=bd), ref)
+    pre = torch.empty_like(out)
+    close_bf16(Kn.gemm(xd, wd, out, bias=bd, epi=Kn.EPI_GELU, aux_out=pre), O.gelu(ref))
+    close_bf16(pre, ref)
+    close_bf16(Kn.gemm(xd, wd, out, bias=bd, epi=Kn.EPI_ADD, aux=resd), ref + res)
+    out32 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    Kn.gemm(xd, wd, out32, bias=bd, epi=Kn.EPI_ADD, aux=res.to(dev))
+    assert rel_l2(out32.cpu(), ref + res) < 1e-5
+
+
+def test_linear_backward_gemms(dev):
+    """dgrad (MN-major B), fused dGELU, wgrad (both operands MN-major, split-K reduce-add) vs fp64 autograd."""
+    from jepa_b200 import kernels as Kn
+    from oracle import vjepa_oracle as O
+    T, Din, Dout = 520, 192, 768
+    g = torch.Generator().manual_seed(5)
+    x, w = bf(torch.randn(T, Din, generator=g)), bf(torch.randn(Dout, Din, generator=g) * 0.05)
+    dy, hpre = bf(torch.randn(T, Dout, generator=g)), bf(torch.randn(T, Dout, generator=g))
+    xd, wd, dyd, hd_ = (t.to(dev, torch.bfloat16) for t in (x, w, dy, hpre))
+    dx = torch.empty(T, Din, dtype=torch.bfloat16, device=dev)
+    close_bf16(Kn.gemm(dyd, wd, dx, b_mn=True), dy @ w, atol=5e-2)
+    # dGELU epilogue: (dz @ W2) * gelu'(h) where W2 [Din, Dout] maps hidden(Dout) -> Din
+    w2 = bf(torch.randn(Din, Dout, generator=g) * 0.05)
+    dz = bf(torch.randn(T, Din, generator=g))
+    hh = hpre.double().requires_grad_(True)
+    O.gelu(hh).backward((dz @ w2).double())
+    dh = torch.empty(T, Dout, dtype=torch.bfloat16, device=dev)
+    close_bf16(Kn.gemm(dz.to(dev, torch.bfloat16), w2.to(dev, torch.bfloat16), dh, b_mn=True, epi=Kn.EPI_DGELU, aux=hd_),
+               hh.grad.float(), atol=3e-2)
+    # wgrad accumulates into fp32
+    dw0 = torch.randn(Dout, Din, generator=g)
+    dw = dw0.clone().to(dev)
+    Kn.gemm(dyd, xd, dw, a_mn=True, b_mn=True, accumulate=True, split_k=3)
+    assert rel_l2(dw.cpu(), dw0 + dy.t() @ x) < 1e-5
+    db = torch.zeros(Dout, device=dev)
+    Kn.colsum(dyd, db)
+    assert rel_l2(db.cpu(), dy.sum(0)) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------- rows
+@pytest.mark.parametrize("D", [192, 384, 1024, 1280])
+def test_layernorm_fwd_bwd(dev, D):
+    from jepa_b200 import kernels as Kn
+    from oracle import vjepa_oracle as O
+    T = 777
+    g = torch.Generator().manual_seed(D)
+    x = bf(torch.randn(T, D, generator=g) * 2 + 0.5)
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    dy, dres = bf(torch.randn(T, D, generator=g)), bf(torch.randn(T, D, generator=g))
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    y = O.layer_norm(xr, wr, br, 1e-6)
+    y.backward(dy.double())
+    xd = x.to(dev, torch.bfloat16)
+    yd = torch.empty_like(xd)
+    mean, rstd = torch.empty(T, device=dev), torch.empty(T, device=dev)
+    Kn.layernorm_fwd(xd, yd, w.to(dev), b.to(dev), 1e-6, mean, rstd)
+    close_bf16(yd, y.detach().float())
+    assert rel_l2(mean.cpu(), x.mean(-1)) < 1e-5
+    dx = torch.empty_like(xd)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    Kn.layernorm_bwd(dy.to(dev, torch.bfloat16), xd, w.to(dev), mean, rstd, dres.to(dev, torch.bfloat16), dx, dg, db)
+    close_bf16(dx, (xr.grad + dres.double()).float(), atol=3e-2)
+    assert rel_l2(dg.cpu(), wr.grad.float()) < 1e-4 and rel_l2(db.cpu(), br.grad.float()) < 1e-4
+    # fp32 in / fp32 out variant
+    y32 = torch.empty(T, D, device=dev)
+    Kn.layernorm_fwd(x.to(dev), y32, w.to(dev), b.to(dev), 1e-6)
+    assert rel_l2(y32.cpu(), y.detach().float()) < 1e-5
+
+
+def test_gather_paths_bit_exact(dev):
+    from jepa_b200 import kernels as Kn
+    from src.masks.utils import apply_masks
+    from oracle import vjepa_oracle as O
+    B, N, D = 3, 784, 192
+    me, mp = c1_masks(2)
+    idx = torch.cat([me[0], me[0][:1].flip(1)], 0)  # also a descending row
+    for dt in (torch.float32, torch.bfloat16):
+        x = torch.randn(B, N, D).to(dt)
+        ref = O.apply_masks(x, [idx])
+        got = Kn.gather_rows(x.to(dev), idx.to(dev))
+        assert torch.equal(got.cpu(), ref)
+        assert torch.equal(apply_masks(x.to(dev), [idx.to(dev)]).cpu(), ref)
+    # empty / ragged: K = 0 rows is a no-op that returns an empty tensor
+    assert Kn.gather_rows(x.to(dev), torch.zeros(B, 0, dtype=torch.int64, device=dev)).shape == (B, 0, D)
+    # scatter-add is the exact adjoint on unique indices
+    dy = torch.randn(B, idx.shape[1], D)
+    dx = torch.zeros(B, N, D, device=dev)
+    Kn.scatter_rows_add(dy.to(dev), dx, idx.to(dev))
+    ref = torch.zeros(B, N, D)
+    ref.scatter_add_(1, idx.unsqueeze(-1).expand(-1, -1, D), dy)
+    assert torch.equal(dx.cpu(), ref)
+
+
+def test_patch_embed_matches_oracle(dev):
+    from jepa_b200 import kernels as Kn
+    from oracle import vjepa_oracle as O
+    B, T, H = 2, 8, 224
+    D, P = 192, 1536
+    g = torch.Generator().manual_seed(1)
+    clips = synth_clips(B, T, H, H, seed=3)
+    w = bf(torch.randn(D, 3, 2, 16, 16, generator=g) * 0.03)
+    b = torch.randn(D, generator=g) * 0.02
+    pos = torch.randn(784, D, generator=g)
+    me, _ = c1_masks(B)
+    ref_all = O.patch_embed_3d(bf(clips), w, b) + pos
+    patches = torch.empty(B * 784, P, dtype=torch.bfloat16, device=dev)
+    Kn.im2col_tubelets(clips.to(dev), patches, None, 2, 16)
+    out = torch.empty(B * 784, D, dtype=torch.bfloat16, device=dev)
+    Kn.gemm(patches, w.reshape(D, P).to(dev, torch.bfloat16), out, bias=b.to(dev), epi=Kn.EPI_ADD, aux=pos.to(dev), aux_period=784)
+    close_bf16(out.view(B, 784, D), ref_all, atol=3e-2)
+    # gather-first context path: identical rows to embedding everything and gathering afterwards
+    m = me[0].to(dev)
+    Kk = m.shape[1]
+    pk = torch.empty(B * Kk, P, dtype=torch.bfloat16, device=dev)
+    Kn.im2col_tubelets(clips.to(dev), pk, m, 2, 16)
+    assert torch.equal(pk.view(B, Kk, P), Kn.gather_rows(patches.view(B, 784, P), m))
+    outk = torch.empty(B * Kk, D, dtype=torch.bfloat16, device=dev)
+    Kn.gemm(pk, w.reshape(D, P).to(dev, torch.bfloat16), outk, bias=b.to(dev), epi=Kn.EPI_ADD, aux=pos.to(dev),
+            aux_rowmap=m.reshape(-1).to(torch.int32))
+    assert torch.equal(outk.view(B, Kk, D), Kn.gather_rows(out.view(B, 784, D), m))
+
+
+@pytest.mark.parametrize("H,hd,lens", [(3, 64, [208, 160]), (16, 24, [296, 40, 128]), (3, 128, [200, 72])])
+def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
+    """Attention (modules.py:61-78 core) incl. the zero-padded hd=24 heads, ragged sequence tails."""
+    from jepa_b200 import kernels as Kn
+    from jepa_b200.params import padded_head_dim
+    hdp = padded_head_dim(hd)
+    T = sum(lens)
+    g = torch.Generator().manual_seed(hd)
+    q, k, v, do = (bf(torch.randn(T, H, hd, generator=g)) for _ in range(4))
+    qkv = torch.zeros(T, 3, H, hdp)
+    qkv[:, 0, :, :hd], qkv[:, 1, :, :hd], qkv[:, 2, :, :hd] = q, k, v
+    dop = torch.zeros(T, H, hdp)
+    dop[..., :hd] = do
+    cu = torch.tensor([0] + [sum(lens[:i + 1]) for i in range(len(lens))], dtype=torch.int32, device=dev)
+    qkv_d = qkv.reshape(T, 3 * H * hdp).to(dev, torch.bfloat16)
+    out = torch.empty(T, H * hdp, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(H, T, device=dev)
+    scale = hd ** -0.5
+    Kn.attn_fwd(qkv_d, out, lse, cu, len(lens), max(lens), H, hdp, scale)
+    dqkv = torch.empty_like(qkv_d)
+    Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dqkv, cu,
+                len(lens), max(lens), H, hdp, scale)
+    out_c, dq_c = out.float().cpu().view(T, H, hdp), dqkv.float().cpu().view(T, 3, H, hdp)
+    assert float(out_c[..., hd:].abs().max()) == 0 and float(dq_c[..., hd:].abs().max()) == 0
+    off = 0
+    for L in lens:
+        qq, kk, vv = (t[off:off + L].double().transpose(0, 1).requires_grad_(True) for t in (q, k, v))  # [H, L, hd]
+        att = torch.softmax((qq @ kk.transpose(-2, -1)) * scale, dim=-1)
+        o = att @ vv
+        o.backward(do[off:off + L].double().transpose(0, 1))
+        close_bf16(out_c[off:off + L, :, :hd], o.detach().transpose(0, 1).float())
+        for i, t in enumerate((qq, kk, vv)):
+            close_bf16(dq_c[off:off + L, i, :, :hd], t.grad.transpose(0, 1).float(), atol=3e-2, rtol=2e-2)
+        off += L
+
+
+def test_target_ln_gather_and_loss(dev):
+    from jepa_b200 import kernels as Kn
+    from jepa_b200 import step as vj
+    from jepa_b200.models import _token_views
+    from oracle import vjepa_oracle as O
+    B, N, D = 2, 784, 192
+    g = torch.Generator().manual_seed(9)
+    x = bf(torch.randn(B, N, D, generator=g) * 3)
+    w, b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    _, mp = c1_masks(B)
+    ref = O.apply_masks(O.layer_norm(O.layer_norm(x, w, b, 1e-6), None, None, 1e-5), mp, concat=False)
+    for m, r in zip(mp, ref):
+        got = Kn.target_ln_gather(x.to(dev, torch.bfloat16), m.to(dev), w.to(dev), b.to(dev), 1e-6, 1e-5)
+        assert rel_l2(got.cpu(), r) < 1e-5
+    # L1 loss forward/backward vs autograd
+    sizes = [int(m.shape[1]) for m in mp]
+    z = [bf(torch.randn(B, k, D, generator=g)) for k in sizes]
+    zc = torch.cat([t.reshape(-1, D) for t in z]).to(dev, torch.bfloat16).requires_grad_(True)
+    hc = torch.cat([t.reshape(-1, D) for t in ref]).to(dev)
+    loss = vj.jepa_loss(_token_views(zc, B, sizes), _token_views(hc, B, sizes))
+    (loss * 65536.0).backward()
+    zr = [t.clone().requires_grad_(True) for t in z]
+    lref = O.loss_fn(zr, ref)
+    (lref * 65536.0).backward()
+    assert abs(float(loss) - float(lref)) < 1e-5
+    close_bf16(zc.grad, torch.cat([t.grad.reshape(-1, D) for t in zr]), atol=1e-6, rtol=1e-2)
+    assert abs(float(vj.reg_loss([t.to(dev, torch.bfloat16) for t in z])) - float(O.reg_fn(z))) < 1e-4
+
+
+def test_ema_bit_exact_and_adamw(dev):
+    from jepa_b200 import kernels as Kn
+    from jepa_b200.optim import FlatAdamW
+    g = torch.Generator().manual_seed(4)
+    n = 4096 * 3 + 64
+    k, q = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    for m in (0.998, 0.99925, 1.0):
+        kd = k.clone().to(dev)
+        Kn.ema_update(kd, q.to(dev), m)
+        ref = k.clone()
+        ref.mul_(m).add_((1. - m) * q)       # the reference's op sequence, train.py:486-487
+        assert torch.equal(kd.cpu(), ref), m
+    # AdamW vs torch.optim.AdamW (fp32 CPU) over several steps, incl. weight decay and a skipped step
+    p0, grads = torch.randn(256, 64, generator=g), [torch.randn(256, 64, generator=g) for _ in range(4)]
+    pr = torch.nn.Parameter(p0.clone())
+    ref_opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    pc = torch.nn.Parameter(p0.clone().to(dev))
+    opt = FlatAdamW([pc], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    for gr in grads:
+        pr.grad = gr.clone(); ref_opt.step()
+        pc.grad = gr.clone().to(dev); opt.step()
+    assert rel_l2(pc.detach().cpu(), pr.detach()) < 1e-6
+    before = pc.detach().clone()
+    opt.found_inf = torch.ones((), device=dev)
+    pc.grad = grads[0].to(dev); opt.step()
+    del opt.found_inf
+    assert torch.equal(pc.detach(), before)
+
+
+def test_cast_and_head_pad_round_trip(dev):
+    from jepa_b200 import kernels as Kn
+    w = torch.randn(3 * 16 * 24, 384)
+    wd = w.to(dev)
+    sh = torch.empty(w.numel(), dtype=torch.bfloat16, device=dev)
+    Kn.cast_f32_bf16(wd.view(-1), sh)
+    assert torch.equal(sh.cpu(), w.view(-1).to(torch.bfloat16))
+    pad = torch.empty(3 * 16 * 32, 384, dtype=torch.bfloat16, device=dev)
+    Kn.head_pad(wd, pad, 1, 48, 24, 32, 384)
+    pv = pad.cpu().view(48, 32, 384)
+    assert torch.equal(pv[:, :24], w.to(torch.bfloat16).view(48, 24, 384)) and float(pv[:, 24:].abs().max()) == 0
+    gpad = torch.randn(3 * 16 * 32, 384)
+    acc = torch.ones(3 * 16 * 24, 384, device=dev)
+    Kn.head_pad(gpad.to(dev), acc, 1, 48, 24, 32, 384, unpad_add=True)
+    assert torch.equal(acc.cpu(), 1 + gpad.view(48, 32, 384)[:, :24].reshape(-1, 384))
+    # proj-style padding along columns
+    wp = torch.randn(384, 16 * 24)
+    pp = torch.empty(384, 16 * 32, dtype=torch.bfloat16, device=dev)
+    Kn.head_pad(wp.to(dev), pp, 384, 16, 24, 32, 1)
+    assert torch.equal(pp.cpu().view(384, 16, 32)[:, :, :24], wp.to(torch.bfloat16).view(384, 16, 24))
+
+
+# --------------------------------------------------------------------------------------------- networks
+def test_c1_step_shallow_vs_oracle(dev):
+    """2+2 layer ViT-Tiny step: isolates wiring errors from depth-accumulated rounding."""
+    got = run_c1_step_cuda(dev, batch=2, depth_limit=2)
+    ref = run_c1_step_oracle(batch=2, depth_limit=2)
+    compare_step(got, ref, verbose=True, tol_act=1.5e-2, tol_grad=3e-2)
+
+
+def test_c1_step_full_vs_oracle_and_golden(dev, golden_dir):
+    """BASELINE config[0]: ViT-Tiny/16, 2 clips, 8x224x224, multiblock3d masks, one full train step."""
+    got = run_c1_step_cuda(dev)
+    ref = run_c1_step_oracle()
+    compare_step(got, ref, verbose=True)
+    gold = torch.load(os.path.join(golden_dir, "golden_step_c1.pt"))
+    assert abs(got["loss_jepa"] - gold["loss_jepa"]) < 5e-3
+    for key, gkey in (("h", "h"), ("z", "z"), ("z_enc", "zenc")):
+        for i, t in enumerate(got[key]):
+            assert rel_l2(t[:, :4, :16], gold[f"{gkey}_slices"][i]) < 2 * TOL_ACT
+            assert abs(float(t.norm()) - gold[f"{gkey}_norm"][i]) / gold[f"{gkey}_norm"][i] < TOL_ACT
+    for key in ("enc", "pred"):
+        for n, refn in gold[f"{key}_grad_norm"].items():
+            assert abs(float(got[f"{key}_grad"][n].norm()) - refn) <= 6e-2 * refn + 1e-9, n
+    for n, ref_slice in gold["ema_slices"].items():
+        assert torch.equal(got["ema"][n].reshape(-1)[:32], ref_slice), n
+
+
+def test_multimask_fused_equals_per_mask_calls(dev):
+    """MultiMaskWrapper semantics (multimask.py:17-26): the fused var-len pass == one backbone call per mask."""
+    from jepa_b200.models import vit_tiny
+    torch.manual_seed(0)
+    enc = vit_tiny(img_size=224, patch_size=16, num_frames=8, tubelet_size=2, uniform_power=True).to(dev)
+    clips = synth_clips(2, 8, 224, 224, seed=1).to(dev)
+    me, _ = c1_masks(2)
+    me = [m.to(dev) for m in me]
+    with torch.no_grad():
+        fused = enc.forward_multi(clips, me)
+        single = [enc(clips, masks=m) for m in me]
+        full = enc(clips)
+    for a, b in zip(fused, single):
+        assert torch.equal(a, b)
+    assert full.shape == (2, 784, 192)
+    cat = enc(clips, masks=[me[0], me[0]])
+    assert cat.shape == (4, me[0].shape[1], 192) and torch.equal(cat[:2], cat[2:])
+
+
+# --------------------------------------------------------------------------------------------- full size
+def test_full_size_properties_vitl(dev):
+    """BASELINE config[1] shapes (ViT-L/16, B=32, 16x224^2): properties that do not need a CPU oracle pass."""
+    from jepa_b200 import kernels as Kn
+    T, D, Hd = 32 * 1568, 1024, 4096
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(T, D, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Hd, D, device=dev, generator=g) * 0.03).to(torch.bfloat16)
+    y1 = torch.empty(T, Hd, dtype=torch.bfloat16, device=dev)
+    y2 = torch.empty_like(y1)
+    Kn.gemm(x, w, y1)
+    Kn.gemm(x, w, y2, alpha=2.0)                      # linearity: exact in bf16 (power-of-two scale)
+    assert torch.equal((y1.float() * 2).to(torch.bfloat16), y2)
+    rows = torch.tensor([0, 1, 127, 128, 25087, 50175], device=dev)
+    ref = x[rows].double() @ w.double().t()           # sampled rows in fp64
+    close_bf16(y1[rows], ref.float().cpu(), atol=3e-2)
+    # LayerNorm output rows are standardised
+    yn = torch.empty_like(x)
+    Kn.layernorm_fwd(x, yn, torch.ones(D, device=dev), torch.zeros(D, device=dev), 1e-6)
+    s = yn[::997].float()
+    assert float(s.mean(-1).abs().max()) < 1e-2 and float((s.var(-1, unbiased=False) - 1).abs().max()) < 3e-2
+    # attention over full-length sequences: softmax rows are convex combinations -> |O| <= max|V|, and constant V is a fixed point
+    H, hd, S, B = 16, 64, 1568, 4
+    qkv = torch.randn(B * S, 3 * H * hd, device=dev, generator=g).to(torch.bfloat16)
+    qkv[:, 2 * H * hd:] = 0.5
+    out = torch.empty(B * S, H * hd, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(H, B * S, device=dev)
+    cu = torch.arange(0, (B + 1) * S, S, dtype=torch.int32, device=dev)
+    Kn.attn_fwd(qkv, out, lse, cu, B, S, H, hd, hd ** -0.5)
+    assert float((out.float() - 0.5).abs().max()) < 4e-3
+    # gather / scatter-add round trip at full size is the identity on kept rows
+    N, Kk = 1568, 360
+    idx = torch.stack([torch.randperm(N, device=dev, generator=g)[:Kk].sort().values for _ in range(32)])
+    xx = torch.randn(32, N, D, device=dev, generator=g)
+    gat = Kn.gather_rows(xx, idx)
+    back = torch.zeros_like(xx)
+    Kn.scatter_rows_add(gat, back, idx)
+    assert torch.equal(Kn.gather_rows(back, idx), gat)
+    assert float(back.abs().sum(-1).ne(0).sum()) == 32 * Kk

@@ -1,0 +1,48 @@
+"""Pin the oracle: its fp32 C1 step must reproduce what the UNMODIFIED reference produced on the same
+seeded weights / clips / masks (tests/golden/golden_step_c1.pt, written by tests/golden/make_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from parity_util import run_c1_step_oracle, rel_l2
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return torch.load(os.path.join(golden_dir, "golden_step_c1.pt"))
+
+
+@pytest.fixture(scope="module")
+def oracle_step():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    return run_c1_step_oracle()
+
+
+def test_losses(gold, oracle_step):
+    assert abs(oracle_step["loss_jepa"] - gold["loss_jepa"]) < 2e-5
+    assert abs(oracle_step["loss_reg"] - gold["loss_reg"]) < 2e-5
+
+
+def test_activations(gold, oracle_step):
+    for key, gkey in (("h", "h"), ("z", "z"), ("z_enc", "zenc")):
+        for i, t in enumerate(oracle_step[key]):
+            assert rel_l2(t[:, :4, :16], gold[f"{gkey}_slices"][i]) < 2e-4, key
+            assert abs(float(t.norm()) - gold[f"{gkey}_norm"][i]) / gold[f"{gkey}_norm"][i] < 2e-4, key
+
+
+def test_gradients(gold, oracle_step):
+    for key in ("enc", "pred"):
+        norms, slices = gold[f"{key}_grad_norm"], gold[f"{key}_grad_slices"]
+        grads = oracle_step[f"{key}_grad"]
+        assert set(norms) == set(grads)
+        for n, ref in norms.items():
+            assert abs(float(grads[n].norm()) - ref) <= 2e-3 * ref + 1e-9, (n, float(grads[n].norm()), ref)
+        for n, ref in slices.items():
+            got = grads[n].reshape(-1)[:32]
+            assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-9, n
+
+
+def test_ema(gold, oracle_step):
+    for n, ref in gold["ema_slices"].items():
+        assert torch.equal(oracle_step["ema"][n].reshape(-1)[:32], ref), n
