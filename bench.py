@@ -239,6 +239,10 @@ def run_ours(args):
         ms_total = float(t)
     ms_step = ms_total / args.steps
     value = B * world / (ms_step * 1e-3)
+    if args.profile:   # run under ncu: only the bare steps, no auxiliary passes
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": int(launches)}), flush=True)
+        return
 
     # ---- per-launch GEMM timing inside further steps (roofline of the dominant kernel) -------------
     from jepa_b200 import kernels as Kn
@@ -353,6 +357,7 @@ def oracle_step_fn(cfg_name, B):
     """Returns a closure running ONE fp32 train step (target fwd, context+predictor fwd/bwd, loss, EMA) of the
     oracle on B clips.  AdamW is omitted on the CPU side (a few % of the CPU step), which favours the baseline."""
     from oracle import vjepa_oracle as O
+    O.FUSED = True   # torch's fused CPU operators, i.e. the library calls the reference itself makes on CPU
     from jepa_b200.models import VisionTransformer, vit_predictor
     from functools import partial
     import torch.nn as nn
@@ -387,8 +392,28 @@ def oracle_step_fn(cfg_name, B):
     return step
 
 
+def usable_cores():
+    """Host threads this process can really use: min(os.cpu_count, sched affinity, cgroup cpu quota), capped at
+    VJ_CPU_THREADS if set (oversubscribing a quota-limited container is several times slower than matching it)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    if os.environ.get("VJ_CPU_THREADS"):
+        n = min(n, int(os.environ["VJ_CPU_THREADS"]))
+    return max(1, min(n, 64))   # torch intra-op scaling of this workload saturates well before 64 threads
+
+
 def cpu_baseline(cfg_name, budget_s=25.0):
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     B = 1
     step = oracle_step_fn(cfg_name, B)
@@ -410,7 +435,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     model_name, D, L, heads, crop, frames, Bcfg = CONFIGS[args.config]
     B = 1
@@ -452,6 +477,7 @@ def main():
     ap.add_argument("--config", default="vitl16", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bare steps only (for ncu); never a bench value")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
@@ -459,7 +485,9 @@ def main():
         run_reference(args)
     else:
         args.steps = args.steps if args.steps is not None else 20
-        args.warmup = max(3, args.warmup if args.warmup is not None else 5)
+        args.warmup = args.warmup if args.warmup is not None else 5
+        if not args.profile:
+            args.warmup = max(3, args.warmup)
         run_ours(args)
 
 

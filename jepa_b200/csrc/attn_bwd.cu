@@ -209,11 +209,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       {
         const int qrow = i * 128 + tid;
         const bool ok = qrow < len;
-        lse_s[tid] = ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : 0.f;
+        // +inf for rows past the sequence end -> ex2(s - inf) = 0: invalid queries drop out without predicates
+        lse_s[tid] = ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : INFINITY;
         del_s[tid] = ok ? p.delta[(long long)head * p.T + row_begin + qrow] : 0.f;
       }
       named_bar_sync_attn(1, 128);
-      const int qvalid = min(128, len - i * 128);
       // the P/dS tile is free once the previous iteration's dK MMA retired
       if (i > 0) mbar_wait(bar_qdofree, (i - 1) & 1);
       mbar_wait(bar_s, ph);
@@ -225,13 +225,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tmem_ld32(tmem_ST + lane_addr + c * 32, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int q0i = c * 32 + e;
-          float a = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_s[q0i]));
-          float b = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_s[q0i + 1]));
-          a = q0i < qvalid ? a : 0.f;
-          b = q0i + 1 < qvalid ? b : 0.f;
-          pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+        for (int e = 0; e < 32; e += 4) {
+          const float4 L = *reinterpret_cast<const float4*>(&lse_s[c * 32 + e]);
+          const float a0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x));
+          const float a1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y));
+          const float a2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z));
+          const float a3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w));
+          pk[c * 16 + e / 2] = pack_bf16x2(a0, a1);
+          pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3);
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -251,12 +252,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tmem_wait_ld();
         uint32_t ds[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int q0i = c * 32 + e;
-          const uint32_t pp = pk[c * 16 + e / 2];
-          const float a = bf16_lo(pp) * (__uint_as_float(v[e]) - del_s[q0i]);
-          const float b = bf16_hi(pp) * (__uint_as_float(v[e + 1]) - del_s[q0i + 1]);
-          ds[e / 2] = pack_bf16x2(a, b);
+        for (int e = 0; e < 32; e += 4) {
+          const float4 Dl = *reinterpret_cast<const float4*>(&del_s[c * 32 + e]);
+          const uint32_t pp0 = pk[c * 16 + e / 2], pp1 = pk[c * 16 + e / 2 + 1];
+          ds[e / 2] = pack_bf16x2(bf16_lo(pp0) * (__uint_as_float(v[e]) - Dl.x),
+                                  bf16_hi(pp0) * (__uint_as_float(v[e + 1]) - Dl.y));
+          ds[e / 2 + 1] = pack_bf16x2(bf16_lo(pp1) * (__uint_as_float(v[e + 2]) - Dl.z),
+                                      bf16_hi(pp1) * (__uint_as_float(v[e + 3]) - Dl.w));
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -392,7 +394,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     uint8_t* dsb = smem + B::PS_OFF;
     const bool row_ok = q0 + r < len;
-    const float lse_r = row_ok ? p.lse2[(long long)head * p.T + row_begin + q0 + r] : 0.f;
+    const float lse_r = row_ok ? p.lse2[(long long)head * p.T + row_begin + q0 + r] : INFINITY;  // -> P row = 0
     const float del_r = row_ok ? p.delta[(long long)head * p.T + row_begin + q0 + r] : 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
@@ -405,14 +407,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_addr + c * 32, v);
         tmem_wait_ld();
+        if (valid == 128) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const int k0i = c * 32 + e;
-          float a = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_r));
-          float b = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_r));
-          a = (row_ok && k0i < valid) ? a : 0.f;
-          b = (row_ok && k0i + 1 < valid) ? b : 0.f;
-          pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+          for (int e = 0; e < 32; e += 2) {
+            const float a = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_r));
+            const float b = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_r));
+            pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int k0i = c * 32 + e;
+            float a = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -lse_r));
+            float b = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -lse_r));
+            a = (k0i < valid) ? a : 0.f;
+            b = (k0i + 1 < valid) ? b : 0.f;
+            pk[c * 16 + e / 2] = pack_bf16x2(a, b);
+          }
         }
       }
       tc_fence_before();

@@ -8,13 +8,16 @@
 // layout the qkv GEMM epilogue writes), O bf16 [T, H*HD], lse2 fp32 [H, T] (log2 domain:
 // m*scale*log2e + log2(l)).  Sequences are row ranges [cu[s], cu[s+1]).
 //
-// One CTA = one 128-row query tile of one (sequence, head):
-//   warp 0 : TMA producer (Q once, then K_j / V_j tiles of 128 keys)
-//   warp 1 : MMA issuer   S = Q K_j^T  (128x128xHD)  and  O_j = P_j V_j (128xHDx128), both into TMEM
-//   warps 2-5 : one thread per query row: online softmax straight out of TMEM (tcgen05.ld), P_j
-//               written as bf16 into a 128B-swizzled K-major smem tile, O accumulated in registers.
-// Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each for HD=64), so one CTA's
-// softmax overlaps the other's MMAs.
+// One CTA = one 128-row query tile of one (sequence, head); two CTAs are resident per SM.
+//   warp 0    : TMA producer (Q once; K_j double-buffered, V_j single-buffered tiles of 128 keys)
+//   warp 1    : MMA issuer.  S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax threads have
+//               pulled S_j out of TMEM, so it overlaps their exp work; O += P_j V_j accumulates in
+//               TMEM across the whole KV loop (V consumed MN-major from the tile it was loaded as).
+//   warps 2-5 : one thread per query row.  S_j is read from TMEM ONCE into registers; row max;
+//               p = ex2(s*scale - m) in place; bf16 P_j goes to a 128B-swizzled K-major smem tile.
+//               The running max is only refreshed (and O / l rescaled in TMEM) when it grew by more
+//               than 2^8 ("lazy rescale"), so the O accumulator normally never leaves TMEM until the
+//               final 1/l normalisation.
 #include "attn_common.cuh"
 #include "vjepa_b200.h"
 
@@ -30,9 +33,22 @@ struct AttnFwdParams {
 };
 
 template <int HD>
+struct FwdCfg {
+  using A = AttnCfg<HD>;
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = A::TILE_BYTES;                // 2 stages
+  static constexpr int V_OFF = 3 * A::TILE_BYTES;
+  static constexpr int P_OFF = 4 * A::TILE_BYTES;
+  static constexpr int BAR_OFF = P_OFF + A::P_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
+  static constexpr int TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
+};
+
+template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   using C = AttnCfg<HD>;
+  using F = FwdCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -43,26 +59,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   if (q0 >= len) return;
   const int n_kv = (len + 127) / 128;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F::BAR_OFF);
   const uint32_t bar_q = smem_u32(bars + 0);
-  const uint32_t bar_k = smem_u32(bars + 1);
-  const uint32_t bar_v = smem_u32(bars + 2);
-  const uint32_t bar_kfree = smem_u32(bars + 3);
-  const uint32_t bar_vfree = smem_u32(bars + 4);
-  const uint32_t bar_s = smem_u32(bars + 5);
-  const uint32_t bar_p = smem_u32(bars + 6);
-  const uint32_t bar_o = smem_u32(bars + 7);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_k0 = smem_u32(bars + 1);      // 2 stages: +0, +8
+  const uint32_t bar_kfree0 = smem_u32(bars + 3);  // 2 stages
+  const uint32_t bar_v = smem_u32(bars + 5);
+  const uint32_t bar_vfree = smem_u32(bars + 6);   // also "PV_j retired": P tile reusable, O readable
+  const uint32_t bar_s = smem_u32(bars + 7);
+  const uint32_t bar_sfree = smem_u32(bars + 8);
+  const uint32_t bar_p = smem_u32(bars + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
-    mbar_init(bar_kfree, 1); mbar_init(bar_vfree, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k0, 1); mbar_init(bar_k0 + 8, 1);
+    mbar_init(bar_kfree0, 1); mbar_init(bar_kfree0 + 8, 1);
+    mbar_init(bar_v, 1); mbar_init(bar_vfree, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_sfree, 128); mbar_init(bar_p, 128);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 1) tmem_alloc<F::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -70,8 +88,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
-  const uint32_t sQ = smem_u32(smem + C::Q_OFF), sK = smem_u32(smem + C::K_OFF);
-  const uint32_t sV = smem_u32(smem + C::V_OFF), sP = smem_u32(smem + C::P_OFF);
+  const uint32_t sQ = smem_u32(smem + F::Q_OFF), sK = smem_u32(smem + F::K_OFF);
+  const uint32_t sV = smem_u32(smem + F::V_OFF), sP = smem_u32(smem + F::P_OFF);
   const int HHD = p.H * HD;
 
   if (warp == 0) {
@@ -82,11 +100,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         tma_load_2d(sQ + b * C::BOX_BYTES, &tmQKV, bar_q, head * HD + b * C::BOX_INNER, row_begin + q0);
       for (int j = 0; j < n_kv; ++j) {
         const int kr = row_begin + j * 128;
-        mbar_wait(bar_kfree, (j & 1) ^ 1);
-        mbar_expect_tx(bar_k, C::TILE_BYTES);
+        const int st = j & 1;
+        const uint32_t use = uint32_t(j >> 1) & 1;   // per-stage phase
+        mbar_wait(bar_kfree0 + 8 * st, use ^ 1);
+        mbar_expect_tx(bar_k0 + 8 * st, C::TILE_BYTES);
 #pragma unroll
         for (int b = 0; b < C::NBOX; ++b)
-          tma_load_2d(sK + b * C::BOX_BYTES, &tmQKV, bar_k, HHD + head * HD + b * C::BOX_INNER, kr);
+          tma_load_2d(sK + st * C::TILE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_k0 + 8 * st,
+                      HHD + head * HD + b * C::BOX_INNER, kr);
         mbar_wait(bar_vfree, (j & 1) ^ 1);
         mbar_expect_tx(bar_v, C::TILE_BYTES);
 #pragma unroll
@@ -99,25 +120,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, 0, 1);
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        // S = Q K_j^T
-        mbar_wait(bar_k, j & 1);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(bar_k0 + 8 * st, uint32_t(j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_S, kmajor_desc<HD>(sQ, kk), kmajor_desc<HD>(sK, kk), idesc_s, kk > 0);
-        umma_commit(bar_kfree);
+          umma_f16(tmem_S, kmajor_desc<HD>(sQ, kk), kmajor_desc<HD>(sK + st * C::TILE_BYTES, kk), idesc_s, kk > 0);
+        umma_commit(bar_kfree0 + 8 * st);
         umma_commit(bar_s);
-        // O_j = P_j V_j
+      };
+      mbar_wait(bar_q, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(bar_sfree, j & 1);   // S_j has been pulled into registers
+          issue_qk(j + 1);
+        }
         mbar_wait(bar_p, j & 1);
         mbar_wait(bar_v, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_O, ptile_desc(sP, kk), mnmajor_desc<HD>(sV, kk), idesc_o, kk > 0);
+          umma_f16(tmem_O, ptile_desc(sP, kk), mnmajor_desc<HD>(sV, kk), idesc_o, (j > 0 || kk > 0));
         umma_commit(bar_vfree);
-        umma_commit(bar_o);
       }
     }
     __syncwarp();
@@ -125,86 +151,120 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     const int qd = warp & 3;                 // TMEM lane quarter
     const int r = qd * 32 + lane;            // query row inside the tile
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    uint8_t* prow = smem + C::P_OFF + r * 128;
+    float m_ref = -INFINITY;                 // reference max the accumulators are expressed against
+    float l = 0.f;
+    uint8_t* prow = smem + F::P_OFF + r * 128;
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(128, len - j * 128);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_wait_ld();
+      // ---- S_j -> registers (single TMEM pass), then hand the S columns back to the MMA warp
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(tmem_S + lane_addr + 0, s0);
+      tmem_ld32(tmem_S + lane_addr + 32, s1);
+      tmem_ld32(tmem_S + lane_addr + 64, s2);
+      tmem_ld32(tmem_S + lane_addr + 96, s3);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_sfree);
+      // ---- row max (tail columns of the last block masked out)
+      float mx = -INFINITY;
+      if (valid == 128) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      const float alpha = exp2f((m - mx) * p.scale_log2);  // m = -inf on the first block -> 0
-      const float moff = mx * p.scale_log2;
-      m = mx;
-      l *= alpha;
-      // pass 2: p = exp2(s*scale - m*scale) -> bf16 -> swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_addr + c * 32, v);
-        tmem_wait_ld();
-        float pv[32];
+          mx = fmaxf(fmaxf(mx, __uint_as_float(s0[i])),
+                     fmaxf(__uint_as_float(s1[i]), fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i]))));
+      } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -moff));
-          pv[i] = (c * 32 + i < valid) ? e : 0.f;
-          l += pv[i];
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
-          u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-          u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
-          u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          const int col8 = c * 4 + g;  // 16-byte chunk index along the 128 kv columns
-          *reinterpret_cast<uint4*>(prow + (col8 >> 3) * 16384 + (((col8 & 7) ^ (r & 7)) << 4)) = u;
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
+          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
+          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
+          if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(s3[i]));
         }
       }
+      // ---- lazy rescale: only move the reference max when it would overflow the 2^8 head-room
+      const bool grow = (mx - m_ref) * p.scale_log2 > 8.0f;   // true on the first block (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        if (j > 0) {
+          mbar_wait(bar_vfree, (j - 1) & 1);   // PV_{j-1} retired: O is stable
+          tc_fence_after();
+          const float alpha = grow ? ex2_approx((m_ref - mx) * p.scale_log2) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_addr + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_addr + c * 16, o);
+          }
+          tmem_wait_st();
+          l *= alpha;
+        }
+        if (grow) m_ref = mx;
+      }
+      const float moff = m_ref * p.scale_log2;
+      // ---- p = 2^(s*scale - m), packed to bf16 pairs; the single P tile is free once PV_{j-1} retired
+      const bool full = valid == 128;
+      auto expo = [&](uint32_t (&sv)[32], int base, uint32_t (&out)[16]) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -moff));
+          float b = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -moff));
+          if (!full) {
+            a = (base + i < valid) ? a : 0.f;
+            b = (base + i + 1 < valid) ? b : 0.f;
+          }
+          l += a + b;
+          out[i >> 1] = pack_bf16x2(a, b);
+        }
+      };
+      uint32_t p0[16], p1[16], p2[16], p3[16];
+      expo(s0, 0, p0);
+      expo(s1, 32, p1);
+      expo(s2, 64, p2);
+      expo(s3, 96, p3);
+      if (j > 0) mbar_wait(bar_vfree, (j - 1) & 1);
+      auto put = [&](const uint32_t (&pk)[16], int g0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col8 = g0 + g;
+          *reinterpret_cast<uint4*>(prow + (col8 >> 3) * 16384 + (((col8 & 7) ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+      };
+      put(p0, 0); put(p1, 4); put(p2, 8); put(p3, 12);
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_p);
-      // O accumulate
-      mbar_wait(bar_o, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_addr + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
     }
-    // epilogue: O / l -> bf16, staged through the (now idle) P tile for coalesced stores
+    // ---- epilogue: O / l -> bf16, staged through the (now idle) P tile for coalesced stores
+    mbar_wait(bar_vfree, (n_kv - 1) & 1);
+    tc_fence_after();
     const float inv = 1.0f / l;
     const bool row_ok = q0 + r < len;
-    if (row_ok) p.lse2[(long long)head * p.T + row_begin + q0 + r] = m * p.scale_log2 + log2f(l);
+    if (row_ok) p.lse2[(long long)head * p.T + row_begin + q0 + r] = m_ref * p.scale_log2 + log2f(l);
     constexpr int ORB = HD * 2;               // bytes per output row
     constexpr int CH = ORB / 16;              // 16-byte chunks per row
-    uint8_t* stage = smem + C::P_OFF + (warp - 2) * (32 * ORB);
+    uint8_t* stage = smem + F::P_OFF + (warp - 2) * (32 * ORB);
 #pragma unroll
-    for (int g = 0; g < CH; ++g) {
-      uint4 u;
-      u.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
-      u.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-      u.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-      u.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-      *reinterpret_cast<uint4*>(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4)) = u;
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_addr + c * 16, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[8 * h2 + 0]) * inv, __uint_as_float(o[8 * h2 + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o[8 * h2 + 2]) * inv, __uint_as_float(o[8 * h2 + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o[8 * h2 + 4]) * inv, __uint_as_float(o[8 * h2 + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o[8 * h2 + 6]) * inv, __uint_as_float(o[8 * h2 + 7]) * inv);
+        const int g = 2 * c + h2;
+        *reinterpret_cast<uint4*>(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4)) = u;
+      }
     }
+    tc_fence_before();
     __syncwarp();
     // coalesced write-out: CH lanes cover one row
     constexpr int ROWS_PER_IT = 32 / CH;
@@ -212,23 +272,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     for (int it = 0; it < CH; ++it) {
       const int rr = it * ROWS_PER_IT + lane / CH;
       const int g = lane % CH;
-      const int grow = q0 + qd * 32 + rr;
-      if (grow < len) {
+      const int grow_ = q0 + qd * 32 + rr;
+      if (grow_ < len) {
         const uint4 u = *reinterpret_cast<const uint4*>(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
         *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                  ((long long)(row_begin + grow) * p.ld_out + head * HD) * 2 + g * 16) = u;
+                                  ((long long)(row_begin + grow_) * p.ld_out + head * HD) * 2 + g * 16) = u;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (warp == 1) tmem_dealloc<F::TMEM_COLS>(tmem_base);
 }
 
 template <int HD>
 static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
                            float scale, cudaStream_t s) {
   using C = AttnCfg<HD>;
+  using F = FwdCfg<HD>;
   CUtensorMap tm;
   int rc = make_tmap_2d(&tm, qkv, 0, (uint64_t)3 * H * HD, T, (uint64_t)3 * H * HD * 2, C::BOX_INNER, 128,
                         C::TMAP_SWIZZLE);
@@ -236,7 +297,7 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   auto kern = attn_fwd_kernel<HD>;
   static bool configured = false;
   if (!configured) {
-    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES));
     configured = true;
   }
   AttnFwdParams p;
@@ -244,7 +305,7 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   p.H = H; p.T = T; p.ld_out = (long long)H * HD;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((max_len + 127) / 128, nseq, H);
-  kern<<<grid, kAttnThreads, C::SMEM_BYTES, s>>>(tm, p);
+  kern<<<grid, kAttnThreads, F::SMEM_BYTES, s>>>(tm, p);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
   return 0;

@@ -37,156 +37,6 @@ VJ_DEVINL void store8(void* base, long long elem_off, const float (&v)[8]) {
 }
 
 // =============================================================================================
-// LayerNorm forward: y = (x - mean) * rstd * gamma + beta      (one warp per row)
-// =============================================================================================
-template <bool IN_F32, bool OUT_F32>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, void* __restrict__ y,
-                                                     const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ mean_out,
-                                                     float* __restrict__ rstd_out, int T, int D, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int nvec = D >> 3;  // 8-element chunks per row
-  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < T;
-       row += (long long)gridDim.x * warps_per_block) {
-    float v[kMaxVec][8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        load8<IN_F32>(x, row * D + c * 8, v[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
-      }
-    }
-    const float mean = warp_sum(s) / D;
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          ss += d * d;
-        }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        float g[8], b[8], o[8];
-        load8<true>(gamma, c * 8, g);
-        load8<true>(beta, c * 8, b);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-        store8<OUT_F32>(y, row * D + c * 8, o);
-      }
-    }
-  }
-}
-
-// =============================================================================================
-// LayerNorm backward.  dx = dres + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
-// dgamma/dbeta partial sums per block -> [gridDim.x, D] workspace, reduced by colsum_f32.
-// =============================================================================================
-template <bool X_F32>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const void* __restrict__ dres,
-                                                     void* __restrict__ dx, float* __restrict__ part_dgamma,
-                                                     float* __restrict__ part_dbeta, int T, int D) {
-  extern __shared__ float sm[];  // [2][D] block partials
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  const int nvec = D >> 3;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  float dg[kMaxVec][8], db[kMaxVec][8];
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
-
-  for (long long row = (long long)blockIdx.x * warps_per_block + wib; row < T;
-       row += (long long)gridDim.x * warps_per_block) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[kMaxVec][8], gy[kMaxVec][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        float xv[8], dyv[8], g[8];
-        load8<X_F32>(x, row * D + c * 8, xv);
-        load8<false>(dy, row * D + c * 8, dyv);
-        load8<true>(gamma, c * 8, g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          gy[i][j] = g[j] * dyv[j];
-          s1 += gy[i][j];
-          s2 += gy[i][j] * xh[i][j];
-          dg[i][j] += dyv[j] * xh[i][j];
-          db[i][j] += dyv[j];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
-#pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nvec) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (gy[i][j] - s1 - xh[i][j] * s2);
-        if (dres) {
-          float r[8];
-          load8<X_F32>(dres, row * D + c * 8, r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
-        store8<X_F32>(dx, row * D + c * 8, o);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sm[c * 8 + j], dg[i][j]);
-        atomicAdd(&sm[D + c * 8 + j], db[i][j]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    part_dgamma[(long long)blockIdx.x * D + i] = sm[i];
-    part_dbeta[(long long)blockIdx.x * D + i] = sm[D + i];
-  }
-}
-
-// out[c] += sum_r in[r, c]   (fp32 partials, small R)
-__global__ void colsum_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int r = 0; r < R; ++r) s += in[(long long)r * C + c];
-  out[c] += s;
-}
-
-// =============================================================================================
 // Column sum of a bf16 [T, N] matrix into fp32 out[N] (+=): bias gradients; with a periodic row
 // filter (rows r with lo <= r % period < hi) it is also the mask-token gradient.
 // =============================================================================================
@@ -548,54 +398,6 @@ static int grid_for(long long work_items, int per_block) {
 
 using namespace vj;
 
-extern "C" int vj_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, const float* gamma, const float* beta,
-                                float* mean, float* rstd, int T, int D, float eps, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  VJ_CHECK_ARG(x && y && gamma && beta, "vj_layernorm_fwd: null pointer");
-  VJ_CHECK_ARG(D % 8 == 0 && D <= 8 * 32 * kMaxVec, "vj_layernorm_fwd: D=%d unsupported", D);
-  if (T <= 0) return 0;
-  const int grid = grid_for(T, 8);
-  if (x_f32 && y_f32) ln_fwd_kernel<true, true><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
-  else if (x_f32) ln_fwd_kernel<true, false><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
-  else if (y_f32) ln_fwd_kernel<false, true><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
-  else ln_fwd_kernel<false, false><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
-  VJ_CUDA(cudaGetLastError());
-  vj::count_launch(1);
-  return 0;
-}
-
-extern "C" size_t vj_layernorm_bwd_workspace(int T, int D) {
-  (void)T;
-  return (size_t)2 * num_sms() * 2 * D * sizeof(float);
-}
-
-extern "C" int vj_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean,
-                                const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                void* workspace, size_t ws_bytes, int T, int D, void* stream_) {
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
-  VJ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "vj_layernorm_bwd: null pointer");
-  VJ_CHECK_ARG(D % 8 == 0 && D <= 8 * 32 * kMaxVec, "vj_layernorm_bwd: D=%d unsupported", D);
-  if (T <= 0) return 0;
-  int grid = grid_for(T, 8);
-  if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  VJ_CHECK_ARG(ws_bytes >= (size_t)grid * 2 * D * sizeof(float), "vj_layernorm_bwd: workspace too small");
-  float* pg = reinterpret_cast<float*>(workspace);
-  float* pb = pg + (size_t)grid * D;
-  const size_t smem = 2 * D * sizeof(float);
-  if (x_f32)
-    ln_bwd_kernel<true><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres,
-                                                dx, pg, pb, T, D);
-  else
-    ln_bwd_kernel<false><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres,
-                                                 dx, pg, pb, T, D);
-  VJ_CUDA(cudaGetLastError());
-  vj::count_launch(1);
-  colsum_f32_kernel<<<(D + 127) / 128, 128, 0, s>>>(pg, dgamma, grid, D);
-  colsum_f32_kernel<<<(D + 127) / 128, 128, 0, s>>>(pb, dbeta, grid, D);
-  VJ_CUDA(cudaGetLastError());
-  vj::count_launch(2);
-  return 0;
-}
 
 extern "C" int vj_colsum(const void* in, int in_f32, float* out, long long T, int N, long long ld, int period, int lo,
                          int hi, void* stream_) {
@@ -637,9 +439,9 @@ extern "C" int vj_im2col_tubelets(const float* clips, void* patches, const long 
 extern "C" int vj_gather_rows(const void* x, void* out, const long long* idx, int B, int N, int K, int row_bytes,
                               void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  if (B <= 0 || K <= 0) return 0;  // empty selection: nothing to do (empty tensors carry null pointers)
   VJ_CHECK_ARG(x && out && idx, "vj_gather_rows: null pointer");
   VJ_CHECK_ARG(row_bytes % 16 == 0, "vj_gather_rows: row_bytes must be a multiple of 16");
-  if (B <= 0 || K <= 0) return 0;
   const int vpr = row_bytes / 16;
   gather_rows_kernel<<<grid_for((long long)B * K * vpr, 256), 256, 0, s>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), idx, B, N, K, vpr);

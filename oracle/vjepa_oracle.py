@@ -45,8 +45,17 @@ def pos_embed_3d(embed_dim, grid_size, grid_depth, uniform_power=True):
 # ---------------------------------------------------------------------------------------------
 # primitives
 # ---------------------------------------------------------------------------------------------
+# FUSED = True swaps the hand-written primitives for torch's fused CPU operators (F.layer_norm, F.gelu,
+# F.scaled_dot_product_attention) - exactly the library calls the reference itself makes - so the CPU
+# timing legs of bench.py run at the reference's own CPU speed.  tests/test_oracle_cpu.py checks that
+# both modes agree; parity tests always use the plain (FUSED = False) restatement.
+FUSED = False
+
+
 def layer_norm(x, w, b, eps):
     """nn.LayerNorm / F.layer_norm over the last dim (biased variance)."""
+    if FUSED:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     y = (x - mu) / torch.sqrt(var + eps)
@@ -57,10 +66,14 @@ def layer_norm(x, w, b, eps):
 
 def gelu(x):
     """nn.GELU() exact erf form (src/models/utils/modules.py:26)."""
+    if FUSED:
+        return torch.nn.functional.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
 def linear(x, w, b):
+    if FUSED:
+        return torch.nn.functional.linear(x, w, b)
     return x @ w.t() + b
 
 
@@ -97,6 +110,9 @@ def attention(x, S, pre, heads):
     hd = C // heads
     qkv = linear(x, S[pre + 'qkv.weight'], S[pre + 'qkv.bias']).reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
+    if FUSED:
+        y = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+        return linear(y, S[pre + 'proj.weight'], S[pre + 'proj.bias'])
     att = (q @ k.transpose(-2, -1)) * (hd ** -0.5)
     att = att - att.amax(dim=-1, keepdim=True)
     att = torch.exp(att)

@@ -207,7 +207,8 @@ def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
     Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dqkv, cu,
                 len(lens), max(lens), H, hdp, scale)
     out_c, dq_c = out.float().cpu().view(T, H, hdp), dqkv.float().cpu().view(T, 3, H, hdp)
-    assert float(out_c[..., hd:].abs().max()) == 0 and float(dq_c[..., hd:].abs().max()) == 0
+    if hdp > hd:  # padded lanes stay exactly zero end to end
+        assert float(out_c[..., hd:].abs().max()) == 0 and float(dq_c[..., hd:].abs().max()) == 0
     off = 0
     for L in lens:
         qq, kk, vv = (t[off:off + L].double().transpose(0, 1).requires_grad_(True) for t in (q, k, v))  # [H, L, hd]

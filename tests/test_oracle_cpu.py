@@ -46,3 +46,19 @@ def test_gradients(gold, oracle_step):
 def test_ema(gold, oracle_step):
     for n, ref in gold["ema_slices"].items():
         assert torch.equal(oracle_step["ema"][n].reshape(-1)[:32], ref), n
+
+
+def test_fused_mode_agrees_with_plain_restatement(oracle_step):
+    """bench.py's CPU legs run the oracle with torch's fused CPU operators; same numbers as the plain path."""
+    from oracle import vjepa_oracle as O
+    O.FUSED = True
+    try:
+        fused = run_c1_step_oracle()
+    finally:
+        O.FUSED = False
+    assert abs(fused["loss_jepa"] - oracle_step["loss_jepa"]) < 2e-5
+    for key in ("h", "z"):
+        for a, b in zip(fused[key], oracle_step[key]):
+            assert rel_l2(a, b) < 1e-4
+    for n, g in oracle_step["enc_grad"].items():
+        assert rel_l2(fused["enc_grad"][n], g) < 2e-3, n
