@@ -136,6 +136,11 @@ int vj_ema_update(float* k, const float* q, long long n, float m, float one_minu
 int vj_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, const float* inv_scale_dev, const float* found_inf_dev,
                   void* stream);
+/* AdamW over a whole flat parameter buffer in one launch: group_ids (device uint8 per 64-element block)
+ * select lr / weight decay from the 4-entry HOST tables lr4 / wd4; id 255 = frozen or padding (skipped). */
+int vj_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned char* group_ids, long long n,
+                  const float* lr4, const float* wd4, float beta1, float beta2, float eps, int step,
+                  const float* inv_scale_dev, const float* found_inf_dev, void* stream);
 /* out[0] += sum(x^2) over a flat fp32 buffer (grad-norm statistics, src/utils/logging.py:91-105). */
 int vj_sumsq(const float* x, long long n, float* out, void* stream);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vj_head_pad": (I, [P, I, P, I, L, I, I, I, L, I, P]),
     "vj_ema_update": (I, [P, P, L, F, F, P]),
     "vj_adamw_step": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P, P]),
+    "vj_adamw_flat": (I, [P, P, P, P, P, L, P, P, F, F, F, I, P, P, P]),
     "vj_sumsq": (I, [P, L, P, P]),
 }
 

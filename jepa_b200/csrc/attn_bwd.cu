@@ -29,9 +29,13 @@ struct AttnBwdParams {
 template <int HD>
 struct BwdCfg {
   using A = AttnCfg<HD>;
-  // four [128 x HD] operand tiles + one [128 x 128] bf16 P/dS tile + stats + barriers
+  // two resident [128 x HD] operand tiles (T0, T1), ST stages of the two streamed tiles, one [128 x 128] bf16
+  // P/dS tile, stats, barriers.  The streamed pair is double-buffered when it is small enough (HD <= 32) to keep
+  // two CTAs per SM: its TMA latency then hides behind the previous iteration instead of sitting on the chain.
+  static constexpr int ST = HD <= 32 ? 2 : 1;
   static constexpr int T0 = 0, T1 = A::TILE_BYTES, T2 = 2 * A::TILE_BYTES, T3 = 3 * A::TILE_BYTES;
-  static constexpr int PS_OFF = 4 * A::TILE_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A::TILE_BYTES;
+  static constexpr int PS_OFF = (2 + 2 * ST) * A::TILE_BYTES;
   static constexpr int STAT_OFF = PS_OFF + A::P_BYTES;        // [2][2][128] floats
   static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 128 * 4;
   static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
@@ -42,13 +46,13 @@ struct BwdCfg {
 VJ_DEVINL void named_bar_sync_attn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // write 8 packed bf16 (16 bytes) of row r, 16-byte column chunk col8 (0..15) into a [128x128] K-major tile
-VJ_DEVINL void ptile_store(uint8_t* tile, int r, int col8, const uint4& u) {
-  *reinterpret_cast<uint4*>(tile + (col8 >> 3) * 16384 + r * 128 + (((col8 & 7) ^ (r & 7)) << 4)) = u;
+VJ_DEVINL void ptile_store(uint32_t tile, int r, int col8, const uint4& u) {
+  sts128(tile + (col8 >> 3) * 16384 + r * 128 + (((col8 & 7) ^ (r & 7)) << 4), u);
 }
 
 // coalesced store of a per-warp staged [32 rows x HD] bf16 block to global rows
 template <int HD>
-VJ_DEVINL void store_rows_bf16(uint8_t* stage, const float (&vals)[HD], float mul, int lane, __nv_bfloat16* gbase,
+VJ_DEVINL void store_rows_bf16(uint32_t stage, const float (&vals)[HD], float mul, int lane, __nv_bfloat16* gbase,
                                long long ld, int row_first, int rows_valid) {
   constexpr int ORB = HD * 2, CH = ORB / 16, ROWS_PER_IT = 32 / CH;
 #pragma unroll
@@ -58,7 +62,7 @@ VJ_DEVINL void store_rows_bf16(uint8_t* stage, const float (&vals)[HD], float mu
     u.y = pack_bf16x2(vals[8 * g + 2] * mul, vals[8 * g + 3] * mul);
     u.z = pack_bf16x2(vals[8 * g + 4] * mul, vals[8 * g + 5] * mul);
     u.w = pack_bf16x2(vals[8 * g + 6] * mul, vals[8 * g + 7] * mul);
-    *reinterpret_cast<uint4*>(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4)) = u;
+    sts128(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4), u);
   }
   __syncwarp();
 #pragma unroll
@@ -66,7 +70,7 @@ VJ_DEVINL void store_rows_bf16(uint8_t* stage, const float (&vals)[HD], float mu
     const int rr = it * ROWS_PER_IT + lane / CH;
     const int g = lane % CH;
     if (rr < rows_valid) {
-      const uint4 u = *reinterpret_cast<const uint4*>(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
+      const uint4 u = lds128(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
       *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase) + ((long long)(row_first + rr) * ld) * 2 + g * 16) = u;
     }
   }
@@ -119,14 +123,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   const int n_q = (len + 127) / 128;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B::BAR_OFF);
-  const uint32_t bar_kv = smem_u32(bars + 0), bar_qdo = smem_u32(bars + 1), bar_qdofree = smem_u32(bars + 2);
-  const uint32_t bar_s = smem_u32(bars + 3), bar_p = smem_u32(bars + 4), bar_pvdone = smem_u32(bars + 5);
-  const uint32_t bar_dp = smem_u32(bars + 6), bar_ds = smem_u32(bars + 7);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr int ST = B::ST;
+  const uint32_t bar_kv = smem_u32(bars + 0), bar_qdo = smem_u32(bars + 1), bar_qdofree = smem_u32(bars + 3);
+  const uint32_t bar_s = smem_u32(bars + 5), bar_p = smem_u32(bars + 6), bar_pvdone = smem_u32(bars + 7);
+  const uint32_t bar_dp = smem_u32(bars + 8), bar_ds = smem_u32(bars + 9), bar_psfree = smem_u32(bars + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_qdo, 1); mbar_init(bar_qdofree, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(bar_qdo + 8 * st, 1); mbar_init(bar_qdofree + 8 * st, 1); }
     mbar_init(bar_p, 128); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128);
+    mbar_init(bar_psfree, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); }
@@ -149,12 +156,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tma_load_2d(sV + b * C::BOX_BYTES, &tmQKV, bar_kv, 2 * HHD + head * HD + b * C::BOX_INNER, row_begin + kv0);
       }
       for (int i = 0; i < n_q; ++i) {
-        mbar_wait(bar_qdofree, (i & 1) ^ 1);
-        mbar_expect_tx(bar_qdo, 2 * C::TILE_BYTES);
+        const int st = i % ST;
+        const uint32_t u = uint32_t(i / ST) & 1;
+        mbar_wait(bar_qdofree + 8 * st, u ^ 1);
+        mbar_expect_tx(bar_qdo + 8 * st, 2 * C::TILE_BYTES);
 #pragma unroll
         for (int b = 0; b < C::NBOX; ++b) {
-          tma_load_2d(sQ + b * C::BOX_BYTES, &tmQKV, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + i * 128);
-          tma_load_2d(sDO + b * C::BOX_BYTES, &tmDO, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + i * 128);
+          tma_load_2d(sQ + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_qdo + 8 * st,
+                      head * HD + b * C::BOX_INNER, row_begin + i * 128);
+          tma_load_2d(sDO + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmDO, bar_qdo + 8 * st,
+                      head * HD + b * C::BOX_INNER, row_begin + i * 128);
         }
       }
     }
@@ -166,32 +177,35 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_wait(bar_kv, 0);
       for (int i = 0; i < n_q; ++i) {
         const uint32_t ph = i & 1;
-        mbar_wait(bar_qdo, ph);
+        const int st = i % ST;
+        const uint32_t sQi = sQ + st * B::STAGE_BYTES, sDOi = sDO + st * B::STAGE_BYTES;
+        mbar_wait(bar_qdo + 8 * st, uint32_t(i / ST) & 1);
         tc_fence_after();
         // S^T = K Q_i^T
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_ST, kmajor_desc<HD>(sK, kk), kmajor_desc<HD>(sQ, kk), idesc_128, kk > 0);
+          umma_f16(tmem_ST, kmajor_desc<HD>(sK, kk), kmajor_desc<HD>(sQi, kk), idesc_128, kk > 0);
         umma_commit(bar_s);
         mbar_wait(bar_p, ph);
         tc_fence_after();
         // dV += P^T dO_i
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDO, kk), idesc_hd, (i > 0 || kk > 0));
+          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
         umma_commit(bar_pvdone);
         // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDO, kk), idesc_128, kk > 0);
+          umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
         umma_commit(bar_dp);
         mbar_wait(bar_ds, ph);
         tc_fence_after();
         // dK += dS^T Q_i
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQ, kk), idesc_hd, (i > 0 || kk > 0));
-        umma_commit(bar_qdofree);
+          umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+        umma_commit(bar_qdofree + 8 * st);
+        umma_commit(bar_psfree);
       }
     }
     __syncwarp();
@@ -200,22 +214,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int r = qd * 32 + lane;  // key row inside the tile
     const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-    float* stats = reinterpret_cast<float*>(smem + B::STAT_OFF);
-    uint8_t* ps = smem + B::PS_OFF;
+    const uint32_t stats = smem_u32(smem + B::STAT_OFF);
+    const uint32_t ps = sPS;
     for (int i = 0; i < n_q; ++i) {
       const uint32_t ph = i & 1;
-      float* lse_s = stats + (i & 1) * 256;
-      float* del_s = lse_s + 128;
+      const uint32_t lse_s = stats + (i & 1) * 1024;
+      const uint32_t del_s = lse_s + 512;
       {
         const int qrow = i * 128 + tid;
         const bool ok = qrow < len;
         // +inf for rows past the sequence end -> ex2(s - inf) = 0: invalid queries drop out without predicates
-        lse_s[tid] = ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : INFINITY;
-        del_s[tid] = ok ? p.delta[(long long)head * p.T + row_begin + qrow] : 0.f;
+        sts32f(lse_s + 4 * tid, ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : INFINITY);
+        sts32f(del_s + 4 * tid, ok ? p.delta[(long long)head * p.T + row_begin + qrow] : 0.f);
       }
       named_bar_sync_attn(1, 128);
       // the P/dS tile is free once the previous iteration's dK MMA retired
-      if (i > 0) mbar_wait(bar_qdofree, (i - 1) & 1);
+      if (i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
       mbar_wait(bar_s, ph);
       tc_fence_after();
       uint32_t pk[64];
@@ -226,7 +240,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          const float4 L = *reinterpret_cast<const float4*>(&lse_s[c * 32 + e]);
+          const float4 L = lds128f(lse_s + 4 * (c * 32 + e));
           const float a0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x));
           const float a1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y));
           const float a2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z));
@@ -253,7 +267,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         uint32_t ds[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          const float4 Dl = *reinterpret_cast<const float4*>(&del_s[c * 32 + e]);
+          const float4 Dl = lds128f(del_s + 4 * (c * 32 + e));
           const uint32_t pp0 = pk[c * 16 + e / 2], pp1 = pk[c * 16 + e / 2 + 1];
           ds[e / 2] = pack_bf16x2(bf16_lo(pp0) * (__uint_as_float(v[e]) - Dl.x),
                                   bf16_hi(pp0) * (__uint_as_float(v[e + 1]) - Dl.y));
@@ -269,10 +283,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_arrive(bar_ds);
     }
     // epilogue: dV, dK (x scale) -> bf16 -> dqkv[:, v / k third]
-    mbar_wait(bar_qdofree, (n_q - 1) & 1);
+    mbar_wait(bar_psfree, (n_q - 1) & 1);
     tc_fence_after();
     const int rows_valid = max(0, min(32, len - kv0 - qd * 32));
-    uint8_t* stage = ps + (warp - 2) * (32 * HD * 2);
+    const uint32_t stage = ps + (warp - 2) * (32 * HD * 2);
     float acc[HD];
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
@@ -320,14 +334,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int n_kv = (len + 127) / 128;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B::BAR_OFF);
-  const uint32_t bar_qdo = smem_u32(bars + 0), bar_kv = smem_u32(bars + 1), bar_kvfree = smem_u32(bars + 2);
-  const uint32_t bar_s = smem_u32(bars + 3), bar_sread = smem_u32(bars + 4), bar_dp = smem_u32(bars + 5);
-  const uint32_t bar_ds = smem_u32(bars + 6);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr int ST = B::ST;
+  const uint32_t bar_qdo = smem_u32(bars + 0), bar_kv = smem_u32(bars + 1), bar_kvfree = smem_u32(bars + 3);
+  const uint32_t bar_s = smem_u32(bars + 5), bar_sread = smem_u32(bars + 6), bar_dp = smem_u32(bars + 7);
+  const uint32_t bar_ds = smem_u32(bars + 8), bar_dsfree = smem_u32(bars + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bar_qdo, 1); mbar_init(bar_kv, 1); mbar_init(bar_kvfree, 1); mbar_init(bar_s, 1);
-    mbar_init(bar_sread, 128); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128);
+    mbar_init(bar_qdo, 1); mbar_init(bar_s, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(bar_kv + 8 * st, 1); mbar_init(bar_kvfree + 8 * st, 1); }
+    mbar_init(bar_sread, 128); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128); mbar_init(bar_dsfree, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); }
@@ -350,12 +366,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tma_load_2d(sDO + b * C::BOX_BYTES, &tmDO, bar_qdo, head * HD + b * C::BOX_INNER, row_begin + q0);
       }
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(bar_kvfree, (j & 1) ^ 1);
-        mbar_expect_tx(bar_kv, 2 * C::TILE_BYTES);
+        const int st = j % ST;
+        const uint32_t u = uint32_t(j / ST) & 1;
+        mbar_wait(bar_kvfree + 8 * st, u ^ 1);
+        mbar_expect_tx(bar_kv + 8 * st, 2 * C::TILE_BYTES);
 #pragma unroll
         for (int b = 0; b < C::NBOX; ++b) {
-          tma_load_2d(sK + b * C::BOX_BYTES, &tmQKV, bar_kv, HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
-          tma_load_2d(sV + b * C::BOX_BYTES, &tmQKV, bar_kv, 2 * HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
+          tma_load_2d(sK + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_kv + 8 * st,
+                      HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
+          tma_load_2d(sV + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_kv + 8 * st,
+                      2 * HHD + head * HD + b * C::BOX_INNER, row_begin + j * 128);
         }
       }
     }
@@ -367,24 +387,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_wait(bar_qdo, 0);
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t ph = j & 1;
-        mbar_wait(bar_kv, ph);
+        const int st = j % ST;
+        const uint32_t sKj = sK + st * B::STAGE_BYTES, sVj = sV + st * B::STAGE_BYTES;
+        mbar_wait(bar_kv + 8 * st, uint32_t(j / ST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_S, kmajor_desc<HD>(sQ, kk), kmajor_desc<HD>(sK, kk), idesc_128, kk > 0);
+          umma_f16(tmem_S, kmajor_desc<HD>(sQ, kk), kmajor_desc<HD>(sKj, kk), idesc_128, kk > 0);
         umma_commit(bar_s);
         mbar_wait(bar_sread, ph);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_S, kmajor_desc<HD>(sDO, kk), kmajor_desc<HD>(sV, kk), idesc_128, kk > 0);
+          umma_f16(tmem_S, kmajor_desc<HD>(sDO, kk), kmajor_desc<HD>(sVj, kk), idesc_128, kk > 0);
         umma_commit(bar_dp);
         mbar_wait(bar_ds, ph);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dQ, ptile_desc(sDS, kk), mnmajor_desc<HD>(sK, kk), idesc_hd, (j > 0 || kk > 0));
-        umma_commit(bar_kvfree);
+          umma_f16(tmem_dQ, ptile_desc(sDS, kk), mnmajor_desc<HD>(sKj, kk), idesc_hd, (j > 0 || kk > 0));
+        umma_commit(bar_kvfree + 8 * st);
+        umma_commit(bar_dsfree);
       }
     }
     __syncwarp();
@@ -392,7 +415,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-    uint8_t* dsb = smem + B::PS_OFF;
+    const uint32_t dsb = sDS;
     const bool row_ok = q0 + r < len;
     const float lse_r = row_ok ? p.lse2[(long long)head * p.T + row_begin + q0 + r] : INFINITY;  // -> P row = 0
     const float del_r = row_ok ? p.delta[(long long)head * p.T + row_begin + q0 + r] : 0.f;
@@ -429,7 +452,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       mbar_arrive(bar_sread);
       mbar_wait(bar_dp, ph);
-      if (j > 0) mbar_wait(bar_kvfree, (j - 1) & 1);  // previous dQ MMA done reading the dS tile
+      if (j > 0) mbar_wait(bar_dsfree, (j - 1) & 1);  // previous dQ MMA done reading the dS tile
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -452,7 +475,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(bar_ds);
     }
-    mbar_wait(bar_kvfree, (n_kv - 1) & 1);
+    mbar_wait(bar_dsfree, (n_kv - 1) & 1);
     tc_fence_after();
     float acc[HD];
 #pragma unroll

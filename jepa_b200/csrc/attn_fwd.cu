@@ -44,6 +44,26 @@ struct FwdCfg {
   static constexpr int TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
 };
 
+// p = 2^(s*scale - moff) for 32 score columns, summed into l and packed to bf16 pairs; FULL = no tail masking
+template <bool FULL>
+VJ_DEVINL void exp_pack32(const uint32_t (&sv)[32], int base, int valid, float scale_log2, float moff, float& l,
+                          uint32_t (&out)[16]) {
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -moff));
+    float b = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -moff));
+    if (!FULL) {
+      a = (base + i < valid) ? a : 0.f;
+      b = (base + i + 1 < valid) ? b : 0.f;
+    }
+    l0 += a;
+    l1 += b;
+    out[i >> 1] = pack_bf16x2(a, b);
+  }
+  l += l0 + l1;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
@@ -153,7 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     float m_ref = -INFINITY;                 // reference max the accumulators are expressed against
     float l = 0.f;
-    uint8_t* prow = smem + F::P_OFF + r * 128;
+    const uint32_t prow = sP + r * 128;
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(128, len - j * 128);
       mbar_wait(bar_s, j & 1);
@@ -206,32 +226,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       }
       const float moff = m_ref * p.scale_log2;
       // ---- p = 2^(s*scale - m), packed to bf16 pairs; the single P tile is free once PV_{j-1} retired
-      const bool full = valid == 128;
-      auto expo = [&](uint32_t (&sv)[32], int base, uint32_t (&out)[16]) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -moff));
-          float b = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -moff));
-          if (!full) {
-            a = (base + i < valid) ? a : 0.f;
-            b = (base + i + 1 < valid) ? b : 0.f;
-          }
-          l += a + b;
-          out[i >> 1] = pack_bf16x2(a, b);
-        }
-      };
       uint32_t p0[16], p1[16], p2[16], p3[16];
-      expo(s0, 0, p0);
-      expo(s1, 32, p1);
-      expo(s2, 64, p2);
-      expo(s3, 96, p3);
+      if (valid == 128) {
+        exp_pack32<true>(s0, 0, valid, p.scale_log2, moff, l, p0);
+        exp_pack32<true>(s1, 32, valid, p.scale_log2, moff, l, p1);
+        exp_pack32<true>(s2, 64, valid, p.scale_log2, moff, l, p2);
+        exp_pack32<true>(s3, 96, valid, p.scale_log2, moff, l, p3);
+      } else {
+        exp_pack32<false>(s0, 0, valid, p.scale_log2, moff, l, p0);
+        exp_pack32<false>(s1, 32, valid, p.scale_log2, moff, l, p1);
+        exp_pack32<false>(s2, 64, valid, p.scale_log2, moff, l, p2);
+        exp_pack32<false>(s3, 96, valid, p.scale_log2, moff, l, p3);
+      }
       if (j > 0) mbar_wait(bar_vfree, (j - 1) & 1);
       auto put = [&](const uint32_t (&pk)[16], int g0) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col8 = g0 + g;
-          *reinterpret_cast<uint4*>(prow + (col8 >> 3) * 16384 + (((col8 & 7) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          sts128(prow + (col8 >> 3) * 16384 + (((col8 & 7) ^ (r & 7)) << 4),
+                 make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
         }
       };
       put(p0, 0); put(p1, 4); put(p2, 8); put(p3, 12);
@@ -247,7 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     if (row_ok) p.lse2[(long long)head * p.T + row_begin + q0 + r] = m_ref * p.scale_log2 + log2f(l);
     constexpr int ORB = HD * 2;               // bytes per output row
     constexpr int CH = ORB / 16;              // 16-byte chunks per row
-    uint8_t* stage = smem + F::P_OFF + (warp - 2) * (32 * ORB);
+    const uint32_t stage = sP + (warp - 2) * (32 * ORB);
 #pragma unroll
     for (int c = 0; c < HD / 16; ++c) {
       uint32_t o[16];
@@ -261,7 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         u.z = pack_bf16x2(__uint_as_float(o[8 * h2 + 4]) * inv, __uint_as_float(o[8 * h2 + 5]) * inv);
         u.w = pack_bf16x2(__uint_as_float(o[8 * h2 + 6]) * inv, __uint_as_float(o[8 * h2 + 7]) * inv);
         const int g = 2 * c + h2;
-        *reinterpret_cast<uint4*>(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4)) = u;
+        sts128(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4), u);
       }
     }
     tc_fence_before();
@@ -274,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       const int g = lane % CH;
       const int grow_ = q0 + qd * 32 + rr;
       if (grow_ < len) {
-        const uint4 u = *reinterpret_cast<const uint4*>(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
+        const uint4 u = lds128(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
         *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
                                   ((long long)(row_begin + grow_) * p.ld_out + head * HD) * 2 + g * 16) = u;
       }

@@ -192,6 +192,31 @@ VJ_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
       : "memory");
 }
 
+// Explicit shared-space accesses on 32-bit smem addresses.  Pointers derived from the manually aligned
+// dynamic-smem base lose their address space in the compiler and degrade to generic LD/ST otherwise.
+VJ_DEVINL void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+VJ_DEVINL void sts128f(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+VJ_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+VJ_DEVINL float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+VJ_DEVINL void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+VJ_DEVINL float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // 2^x on the MUFU pipe (ex2.approx.ftz, ~2 ulp): softmax probabilities are rounded to bf16 anyway
 VJ_DEVINL float ex2_approx(float x) {
   float y;

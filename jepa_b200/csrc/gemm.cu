@@ -225,6 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int NCHUNK = COLS_PER_WARP / 32;
     uint8_t* buf = epi_base + ew * kEpiBufBytes;
     const uint32_t buf_u32 = smem_u32(buf);
+    const uint32_t bias_u32 = smem_u32(bias_s);
     const int etid = threadIdx.x - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -238,7 +239,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       named_bar_sync(1, kEpiWarps * 32);
       for (int i = etid; i < BN; i += kEpiWarps * 32)
-        bias_s[i] = (p.bias != nullptr && split == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+        sts32f(bias_u32 + 4 * i, (p.bias != nullptr && split == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f);
       named_bar_sync(1, kEpiWarps * 32);
 
       mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -258,16 +259,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, bias_s[col0 + j]);
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, lds32f(bias_u32 + 4 * (col0 + j)));
 
-        // the staging buffer is free again once the previous TMA store has read it
-        if (lane == 0) tma_wait_group_read<0>();
-        __syncwarp();
+        // Staging: the 4 KB per-warp buffer is one fp32 tile, or two bf16 tiles (bufA = TMA-store source of D,
+        // bufB = aux staging / pre-activation store source).  The wait for the previous chunk's TMA stores to
+        // have READ the buffer is placed as late as possible so it hides behind this chunk's TMEM load + math.
+        const uint32_t bufA = buf_u32, bufB = buf_u32 + 2048;
+        bool waited = false;
+        auto wait_prev_store = [&]() {
+          if (!waited) {
+            if (lane == 0) tma_wait_group_read<0>();
+            __syncwarp();
+            waited = true;
+          }
+        };
 
         if (p.epi == VJ_EPI_ADD || p.epi == VJ_EPI_DGELU) {
-          // coalesced global -> smem of the aux tile (32 rows x 32 cols), then each thread
-          // picks up its own row.
+          // coalesced global -> smem of the aux tile (32 rows x 32 cols), then each thread picks up its own row
           const bool a128 = p.aux_f32 != 0;
+          const uint32_t abuf = (a128 || OUT_F32) ? bufA : bufB;   // bf16 aux next to a bf16 D tile: no TMA ever reads bufB
+          if (a128 || OUT_F32) wait_prev_store();
           const int cpr = a128 ? 8 : 4;  // 16B chunks per row
           const int rows_per_it = 32 / cpr;
           const int ch = lane % cpr;
@@ -286,20 +297,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 val = *reinterpret_cast<const uint4*>(src);
               }
             }
-            *reinterpret_cast<uint4*>(buf + swz_off(r, ch, a128)) = val;
+            sts128(abuf + swz_off(r, ch, a128), val);
           }
           __syncwarp();
           float a[32];
           if (a128) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 x = *reinterpret_cast<const float4*>(buf + swz_off(lane, j, true));
+              const float4 x = lds128f(abuf + swz_off(lane, j, true));
               a[4 * j] = x.x; a[4 * j + 1] = x.y; a[4 * j + 2] = x.z; a[4 * j + 3] = x.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 x = *reinterpret_cast<const uint4*>(buf + swz_off(lane, j, false));
+              const uint4 x = lds128(abuf + swz_off(lane, j, false));
               a[8 * j] = bf16_lo(x.x); a[8 * j + 1] = bf16_hi(x.x);
               a[8 * j + 2] = bf16_lo(x.y); a[8 * j + 3] = bf16_hi(x.y);
               a[8 * j + 4] = bf16_lo(x.z); a[8 * j + 5] = bf16_hi(x.z);
@@ -314,9 +325,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= gelu_grad_fast(a[j]);
           }
-        } else if (p.epi == VJ_EPI_GELU) {
-          if (p.has_auxout) {
-            // pre-activation (needed by the backward) goes out first through the same buffer
+        }
+        bool two_stores = false;
+        if (p.epi == VJ_EPI_GELU) {
+          if (p.has_auxout && !OUT_F32) {
+            // pre-activation (needed by the backward) leaves through bufB, gelu(pre) through bufA, one bulk group
+            wait_prev_store();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -324,27 +338,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              *reinterpret_cast<uint4*>(buf + swz_off(lane, j, false)) = o;
+              sts128(bufB + swz_off(lane, j, false), o);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmX, buf_u32, n0 + col0, row0);
-              tma_commit_group();
-              tma_wait_group_read<0>();
-            }
-            __syncwarp();
+            two_stores = true;
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
         }
 
+        wait_prev_store();
         if (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<float4*>(buf + swz_off(lane, j, true)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
+          for (int j = 0; j < 8; ++j)
+            sts128f(bufA + swz_off(lane, j, true), make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -353,14 +359,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
             o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
             o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            *reinterpret_cast<uint4*>(buf + swz_off(lane, j, OUT128)) = o;
+            sts128(bufA + swz_off(lane, j, false), o);
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (OUT_F32 && p.reduce_add) tma_reduce_add_2d(&tmD, buf_u32, n0 + col0, row0);
-          else tma_store_2d(&tmD, buf_u32, n0 + col0, row0);
+          if (two_stores) tma_store_2d(&tmX, bufB, n0 + col0, row0);
+          if (OUT_F32 && p.reduce_add) tma_reduce_add_2d(&tmD, bufA, n0 + col0, row0);
+          else tma_store_2d(&tmD, bufA, n0 + col0, row0);
           tma_commit_group();
         }
       }

@@ -205,3 +205,64 @@ extern "C" int vj_sumsq(const float* x, long long n, float* out, void* stream_) 
   vj::count_launch(1);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// AdamW over a whole FlatParamStore in ONE launch.  Every 64-element block of the flat buffer carries a
+// group id (uint8): hyper-parameters come from a 4-entry table, id 255 = frozen / padding (skipped).
+// ---------------------------------------------------------------------------------------------------
+namespace vj {
+struct AdamGroups {
+  float lr[4], wd[4];
+};
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                         float4* __restrict__ m, float4* __restrict__ v,
+                                                         const unsigned char* __restrict__ gid, long long n4,
+                                                         AdamGroups hp, float beta1, float beta2, float eps, float bc1,
+                                                         float bc2_sqrt, const float* __restrict__ inv_scale,
+                                                         const float* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0.f) return;
+  const float gs = inv_scale ? *inv_scale : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned id = gid[i >> 4];
+    if (id > 3) continue;
+    const float lr = hp.lr[id];
+    const float step_size = lr / bc1;
+    const float decay = 1.0f - lr * hp.wd[id];
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+#define VJ_ADAM1(c)                                                 \
+  {                                                                 \
+    const float gr = gg.c * gs;                                     \
+    pp.c *= decay;                                                  \
+    mm.c = mm.c + (gr - mm.c) * (1.0f - beta1);                     \
+    vv.c = vv.c * beta2 + (1.0f - beta2) * gr * gr;                 \
+    const float denom = sqrtf(vv.c) / bc2_sqrt + eps;               \
+    pp.c -= step_size * (mm.c / denom);                             \
+  }
+    VJ_ADAM1(x) VJ_ADAM1(y) VJ_ADAM1(z) VJ_ADAM1(w)
+#undef VJ_ADAM1
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+}  // namespace vj
+
+extern "C" int vj_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned char* group_ids, long long n,
+                             const float* lr4, const float* wd4, float beta1, float beta2, float eps, int step,
+                             const float* inv_scale_dev, const float* found_inf_dev, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(p && g && m && v && group_ids && lr4 && wd4, "vj_adamw_flat: null pointer");
+  VJ_CHECK_ARG(n % 64 == 0 && step >= 1, "vj_adamw_flat: n %% 64 == 0 and step >= 1 required");
+  VJ_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                 reinterpret_cast<uintptr_t>(v)) & 15) == 0, "vj_adamw_flat: 16-byte alignment required");
+  if (n <= 0) return 0;
+  vj::AdamGroups hp;
+  for (int i = 0; i < 4; ++i) { hp.lr[i] = lr4[i]; hp.wd[i] = wd4[i]; }   // host arrays
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  vj::adamw_flat_kernel<<<vj::flat_grid(n / 4, 256), 256, 0, s>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), group_ids, n / 4, hp, beta1, beta2, eps, float(bc1), float(sqrt(bc2)),
+      inv_scale_dev, found_inf_dev);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}

@@ -72,9 +72,18 @@ class FlatParamStore:
                 view = flat[o:o + cnt].view(shape)
                 view.copy_(p.data.to(torch.float32))
                 p.data = view
+                p._vj_store, p._vj_name = self, n
         self.flat, self.offsets, self.total, self._params = flat, offsets, off, named
         self.shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
         return self
+
+    def owns(self, p):
+        """True if parameter `p` currently aliases its slice of this store's flat buffer."""
+        name = getattr(p, "_vj_name", None)
+        if self.flat is None or name not in self.offsets:
+            return False
+        off, n, shape = self.offsets[name]
+        return p.data_ptr() == self.flat.data_ptr() + 4 * off and tuple(p.shape) == shape
 
     # -- per-step products ---------------------------------------------------------------------
     def refresh_shadow(self):

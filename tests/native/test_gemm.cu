@@ -232,6 +232,15 @@ int main(int argc, char** argv) {
     perf(4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 1, "wgrad_ctx_fc1");
     perf(1024, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 4, "wgrad_ctx_proj_split4");
     perf(76032, 1536, 384, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_pred");
+    perf(76032, 1536, 384, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_pred");
+    perf(76032, 384, 512, 0, 0, 0, VJ_EPI_ADD, 1, "proj_pred");
+    perf(76032, 384, 1536, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_pred");
+    perf(76032, 1536, 384, 0, 1, 0, VJ_EPI_DGELU, 1, "fc2_dgrad_pred");
+    perf(76032, 384, 1536, 0, 1, 0, VJ_EPI_NONE, 1, "fc1_dgrad_pred");
+    perf(1536, 384, 76032, 1, 1, 1, VJ_EPI_NONE, 4, "fc1_wgrad_pred_split4");
+    perf(384, 1536, 76032, 1, 1, 1, VJ_EPI_NONE, 8, "fc2_wgrad_pred_split8");
+    perf(13056, 1024, 1024, 0, 0, 0, VJ_EPI_ADD, 1, "proj_ctx");
+    perf(13056, 4096, 1024, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_ctx");
   }
   printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL PASSED", fails);
   return fails ? 1 : 0;

@@ -385,3 +385,50 @@ def test_full_size_properties_vitl(dev):
     Kn.scatter_rows_add(gat, back, idx)
     assert torch.equal(Kn.gather_rows(back, idx), gat)
     assert float(back.abs().sum(-1).ne(0).sum()) == 32 * Kk
+
+
+def test_flat_adamw_single_launch_matches_torch(dev):
+    """One vj_adamw_flat launch per backbone (group table per 64 elements) == torch.optim.AdamW with the
+    reference's four parameter groups (app/vjepa/utils.py:173-194); frozen pos_embed untouched."""
+    from app.vjepa.utils import init_opt, init_video_model
+    from jepa_b200 import _lib
+    torch.manual_seed(1)
+    enc, pred = init_video_model(device=dev, patch_size=16, num_frames=8, tubelet_size=2, model_name="vit_tiny",
+                                 crop_size=224, pred_depth=1, pred_embed_dim=384, uniform_power=True,
+                                 use_mask_tokens=True, num_mask_tokens=2, use_sdpa=True)
+    for net in (enc, pred):
+        net.backbone._store.adopt(net.backbone)
+    opt, _, sch, wds = init_opt(enc, pred, iterations_per_epoch=10, start_lr=1e-3, ref_lr=2e-3, warmup=1, num_epochs=2,
+                                wd=0.04, final_wd=0.4)
+    ref_params = {}
+    ref_groups = []
+    for g in opt.param_groups:
+        clones = [torch.nn.Parameter(p.detach().clone()) for p in g["params"]]
+        for p, c in zip(g["params"], clones):
+            ref_params[p] = c
+        ref_groups.append({"params": clones, "weight_decay": g["weight_decay"]})
+    ref = torch.optim.AdamW(ref_groups, betas=(0.9, 0.999), eps=1e-8)
+    pos0 = enc.backbone.pos_embed.detach().clone()
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for it in range(3):
+        lr, wd = sch.step(), wds.step()
+        for rg, g in zip(ref.param_groups, opt.param_groups):
+            rg["lr"], rg["weight_decay"] = g["lr"], g["weight_decay"]
+        for net in (enc, pred):
+            st = net.backbone._store
+            gflat = st.new_grad_buffer()
+            for n, p in net.backbone.named_parameters():
+                if p.requires_grad:
+                    view = st.grad_view(gflat, n)
+                    view.copy_(torch.randn(view.shape, device=dev, generator=gen) * 0.01)
+                    p.grad = view
+                    ref_params[p].grad = view.clone()
+        before = _lib.load().vj_launch_count()
+        opt.step()
+        assert _lib.load().vj_launch_count() - before == 2      # one launch per backbone
+        ref.step()
+    for p, c in ref_params.items():
+        assert rel_l2(p.detach().cpu(), c.detach().cpu()) < 2e-6
+    assert torch.equal(enc.backbone.pos_embed.detach(), pos0)
+    sd = opt.state_dict()
+    assert len(sd["state"]) == len(ref_params) and float(next(iter(sd["state"].values()))["step"]) == 3.0
