@@ -59,10 +59,12 @@ int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* cu_seqlens, 
                 int H, int HD, int T, float scale, void* stream);
 
 /* Backward of the above: dqkv bf16 [T, 3*H*HD] from dout bf16 [T, H*HD]; delta_ws fp32 [H*T] scratch.
+ * dq_acc_ws: optional fp32 [T, H*HD] scratch; when given and HD <= 32 the dQ computation is fused into the
+ * dK/dV kernel (TMA reduce-add of per-key-tile partials) instead of a second recomputing kernel.
  * (autograd of modules.py:66-69). */
 int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
-                void* dqkv, const int* cu_seqlens, int nseq, int max_len, int H, int HD, int T, float scale,
-                void* stream);
+                void* dqkv, float* dq_acc_ws, const int* cu_seqlens, int nseq, int max_len, int H, int HD, int T,
+                float scale, void* stream);
 
 /* LayerNorm over the last dim, one warp per row.  x bf16|fp32 [T,D] -> y bf16|fp32; mean/rstd fp32 [T]
  * (nullable) are saved for the backward.  nn.LayerNorm(eps=1e-6) at modules.py:115,119,

@@ -18,7 +18,7 @@ SIGNATURES = {
     "vj_launch_count": (L, []),
     "vj_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, I, P, F, I, P, L, I, P, I, P, L, I, I, P]),
     "vj_attn_fwd": (I, [P, P, P, P, I, I, I, I, I, F, P]),
-    "vj_attn_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "vj_attn_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, F, P]),
     "vj_layernorm_fwd": (I, [P, I, P, I, P, P, P, P, I, I, F, P]),
     "vj_layernorm_bwd_workspace": (Z, [I, I]),
     "vj_layernorm_bwd": (I, [P, P, I, P, P, P, P, P, P, P, P, Z, I, I, P]),

@@ -37,9 +37,11 @@ struct BwdCfg {
   static constexpr int STAGE_BYTES = 2 * A::TILE_BYTES;
   static constexpr int PS_OFF = (2 + 2 * ST) * A::TILE_BYTES;
   static constexpr int STAT_OFF = PS_OFF + A::P_BYTES;        // [2][2][128] floats
-  static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * 128 * 4;
+  static constexpr bool CAN_FUSE_DQ = HD <= 32;               // S^T + dV + dK + dQ partial fit 256 TMEM columns
+  static constexpr int DQS_OFF = STAT_OFF + 2 * 2 * 128 * 4;  // 4 warps x [32 rows x 32 fp32] dQ-partial staging
+  static constexpr int BAR_OFF = DQS_OFF + (CAN_FUSE_DQ ? 4 * 4096 : 0);
   static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
-  static constexpr int DKV_TMEM = (128 + 2 * HD) <= 256 ? 256 : 512;
+  static constexpr int DKV_TMEM = (128 + (CAN_FUSE_DQ ? 3 : 2) * HD) <= 256 ? 256 : 512;
   static constexpr int DQ_TMEM = (128 + HD) <= 256 ? 256 : 512;
 };
 
@@ -107,10 +109,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // ---------------------------------------------------------------------------------------------
 // dK / dV : CTA = (kv tile, sequence, head)
 // ---------------------------------------------------------------------------------------------
-template <int HD>
+// FUSE_DQ: the CTA also forms dQ_i (partial over this key tile) = dS_i K  - A operand = the dS^T tile read M-major,
+// B = the K tile read MN-major - and reduce-adds it (TMA, fp32) into a global accumulator, which makes the
+// separate dQ kernel (a second exp / S / dP recomputation) unnecessary.
+template <int HD, bool FUSE_DQ>
 __global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                    const AttnBwdParams p) {
+                    const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
   using C = AttnCfg<HD>;
   using B = BwdCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
@@ -132,7 +137,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   if (threadIdx.x == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
     for (int st = 0; st < 2; ++st) { mbar_init(bar_qdo + 8 * st, 1); mbar_init(bar_qdofree + 8 * st, 1); }
-    mbar_init(bar_p, 128); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128);
+    mbar_init(bar_p, 4); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 4);
     mbar_init(bar_psfree, 1);
     fence_mbar_init();
   }
@@ -143,6 +148,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_ST = tmem_base, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 128 + HD;
+  const uint32_t tmem_dQ = tmem_base + 128 + 2 * HD;   // FUSE_DQ only
   const uint32_t sK = smem_u32(smem + B::T0), sV = smem_u32(smem + B::T1);
   const uint32_t sQ = smem_u32(smem + B::T2), sDO = smem_u32(smem + B::T3), sPS = smem_u32(smem + B::PS_OFF);
   const int HHD = p.H * HD;
@@ -204,6 +210,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+        if (FUSE_DQ) {
+          // dQ_i partial [q, hd] = dS_i [q, kv] K [kv, hd]: A = dS^T tile as M-major (q contiguous), B = K MN-major
+          constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16(tmem_dQ, make_smem_desc(sPS + kk * 2048, 16384, 1024, 2), mnmajor_desc<HD>(sK, kk), idesc_dq, kk > 0);
+        }
         umma_commit(bar_qdofree + 8 * st);
         umma_commit(bar_psfree);
       }
@@ -216,6 +229,25 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     const uint32_t stats = smem_u32(smem + B::STAT_OFF);
     const uint32_t ps = sPS;
+    const uint32_t dqs = smem_u32(smem + B::DQS_OFF) + (warp - 2) * 4096;
+    const uint32_t kvmask = (!FUSE_DQ || kv0 + r < len) ? 0xFFFFFFFFu : 0u;
+    auto drain_dq = [&](int qi) {   // dQ partial of query tile qi (lanes = query rows) -> global fp32 accumulator
+      uint32_t v[32];
+      tmem_ld32(tmem_dQ + lane_addr, v);
+      tmem_wait_ld();
+      if (lane == 0) tma_wait_group_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(dqs + lane * 128 + ((j ^ (lane & 7)) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmDQ, dqs, head * HD, row_begin + qi * 128 + qd * 32);
+        tma_commit_group();
+      }
+    };
     for (int i = 0; i < n_q; ++i) {
       const uint32_t ph = i & 1;
       const uint32_t lse_s = stats + (i & 1) * 1024;
@@ -245,8 +277,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           const float a1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y));
           const float a2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z));
           const float a3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w));
-          pk[c * 16 + e / 2] = pack_bf16x2(a0, a1);
-          pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3);
+          // fused dQ sums over key rows, so rows past the sequence end must carry P = dS = 0 (kvmask);
+          // for dK / dV alone they are merely never stored
+          pk[c * 16 + e / 2] = pack_bf16x2(a0, a1) & kvmask;
+          pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3) & kvmask;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -255,7 +289,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      // S^T_i was issued after the dQ MMA of iteration i-1, so that partial is complete: drain it now, off the
+      // MMA warp's critical path (it is busy with dV / dP^T).
+      if (FUSE_DQ && i > 0) drain_dq(i - 1);
       mbar_wait(bar_dp, ph);
       mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
       tc_fence_after();
@@ -280,11 +318,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_ds);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ds);
     }
     // epilogue: dV, dK (x scale) -> bf16 -> dqkv[:, v / k third]
     mbar_wait(bar_psfree, (n_q - 1) & 1);
     tc_fence_after();
+    if (FUSE_DQ) drain_dq(n_q - 1);
     const int rows_valid = max(0, min(32, len - kv0 - qd * 32));
     const uint32_t stage = ps + (warp - 2) * (32 * HD * 2);
     float acc[HD];
@@ -308,6 +348,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
     store_rows_bf16<HD>(stage, acc, p.scale, lane, p.dqkv + HHD + head * HD, 3LL * HHD,
                         row_begin + kv0 + qd * 32, rows_valid);
+    if (FUSE_DQ && lane == 0) tma_wait_group<0>();
     tc_fence_before();
   }
   tc_fence_before();
@@ -343,7 +384,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (threadIdx.x == 0) {
     mbar_init(bar_qdo, 1); mbar_init(bar_s, 1);
     for (int st = 0; st < 2; ++st) { mbar_init(bar_kv + 8 * st, 1); mbar_init(bar_kvfree + 8 * st, 1); }
-    mbar_init(bar_sread, 128); mbar_init(bar_dp, 1); mbar_init(bar_ds, 128); mbar_init(bar_dsfree, 1);
+    mbar_init(bar_sread, 4); mbar_init(bar_dp, 1); mbar_init(bar_ds, 4); mbar_init(bar_dsfree, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); }
@@ -450,7 +491,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_sread);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sread);
       mbar_wait(bar_dp, ph);
       if (j > 0) mbar_wait(bar_dsfree, (j - 1) & 1);  // previous dQ MMA done reading the dS tile
       tc_fence_after();
@@ -473,7 +515,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_ds);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ds);
     }
     mbar_wait(bar_dsfree, (n_kv - 1) & 1);
     tc_fence_after();
@@ -496,9 +539,25 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   if (warp == 1) tmem_dealloc<B::DQ_TMEM>(tmem_base);
 }
 
+// dqkv[:, q third] = bf16(scale * acc)   (acc fp32 [T, H*HD] filled by the fused dK/dV kernel's reduce-adds)
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float4* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+                                                              long long T, int HHD, float scale) {
+  const int v4 = HHD >> 2;
+  const long long total = T * v4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / v4;
+    const int c = int(i % v4) * 4;
+    const float4 a = acc[i];
+    uint2 o;
+    o.x = pack_bf16x2(a.x * scale, a.y * scale);
+    o.y = pack_bf16x2(a.z * scale, a.w * scale);
+    *reinterpret_cast<uint2*>(dqkv + t * 3 * HHD + c) = o;
+  }
+}
+
 template <int HD>
 static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
-                           void* dqkv, const int* cu, int nseq, int max_len, int H, int T, float scale,
+                           void* dqkv, float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale,
                            cudaStream_t s) {
   using C = AttnCfg<HD>;
   using B = BwdCfg<HD>;
@@ -507,13 +566,22 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   if (rc) return rc;
   rc = make_tmap_2d(&tdo, dout, 0, (uint64_t)H * HD, T, (uint64_t)H * HD * 2, C::BOX_INNER, 128, C::TMAP_SWIZZLE);
   if (rc) return rc;
-  auto kdkv = attn_bwd_dkv_kernel<HD>;
+  auto kdkv = attn_bwd_dkv_kernel<HD, false>;
+  auto kdkv_fused = attn_bwd_dkv_kernel<HD, B::CAN_FUSE_DQ>;
   auto kdq = attn_bwd_dq_kernel<HD>;
   static bool configured = false;
   if (!configured) {
     VJ_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
+    VJ_CUDA(cudaFuncSetAttribute(kdkv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
     VJ_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
     configured = true;
+  }
+  const bool fuse = B::CAN_FUSE_DQ && dq_acc != nullptr;
+  CUtensorMap tdq = tdo;
+  if (fuse) {
+    VJ_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)T * H * HD * sizeof(float), s));
+    rc = make_tmap_2d(&tdq, dq_acc, 1, (uint64_t)H * HD, T, (uint64_t)H * HD * 4, 32, 32, 3);
+    if (rc) return rc;
   }
   {
     int g = (T + 7) / 8;
@@ -528,7 +596,18 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   p.cu_seqlens = cu; p.lse2 = lse2; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.H = H; p.T = T; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((max_len + 127) / 128, nseq, H);
-  kdkv<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
+  if (fuse) {
+    kdkv_fused<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
+    VJ_CUDA(cudaGetLastError());
+    long long n4 = (long long)T * H * HD / 4;
+    long long g = (n4 + 255) / 256;
+    if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+    attn_dq_convert_kernel<<<int(g), 256, 0, s>>>(reinterpret_cast<const float4*>(dq_acc), p.dqkv, T, H * HD, scale);
+    VJ_CUDA(cudaGetLastError());
+    vj::count_launch(2);
+    return 0;
+  }
+  kdkv<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
   kdq<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
@@ -540,16 +619,16 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
 }  // namespace vj
 
 extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
-                           void* dqkv, const int* cu_seqlens, int nseq, int max_len, int H, int HD, int T, float scale,
-                           void* stream_) {
+                           void* dqkv, float* dq_acc_ws, const int* cu_seqlens, int nseq, int max_len, int H, int HD,
+                           int T, float scale, void* stream_) {
   using namespace vj;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   VJ_CHECK_ARG(qkv && out && dout && lse2 && delta_ws && dqkv && cu_seqlens, "vj_attn_bwd: null pointer");
   VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_bwd: empty problem");
   switch (HD) {
-    case 32: return launch_attn_bwd<32>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
-    case 64: return launch_attn_bwd<64>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
-    case 128: return launch_attn_bwd<128>(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, T, scale, s);
+    case 32: return launch_attn_bwd<32>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
+    case 64: return launch_attn_bwd<64>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
+    case 128: return launch_attn_bwd<128>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
     default: set_error("vj_attn_bwd: head dim %d unsupported (32/64/128)", HD); return -1;
   }
 }

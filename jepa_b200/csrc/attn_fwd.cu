@@ -96,7 +96,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     mbar_init(bar_k0, 1); mbar_init(bar_k0 + 8, 1);
     mbar_init(bar_kfree0, 1); mbar_init(bar_kfree0 + 8, 1);
     mbar_init(bar_v, 1); mbar_init(bar_vfree, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_sfree, 128); mbar_init(bar_p, 128);
+    mbar_init(bar_s, 1); mbar_init(bar_sfree, 4); mbar_init(bar_p, 4);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
@@ -186,7 +186,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       tmem_ld32(tmem_S + lane_addr + 96, s3);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(bar_sfree);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
       // ---- row max (tail columns of the last block masked out)
       float mx = -INFINITY;
       if (valid == 128) {
@@ -250,7 +251,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       put(p0, 0); put(p1, 4); put(p2, 8); put(p3, 12);
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
     }
     // ---- epilogue: O / l -> bf16, staged through the (now idle) P tile for coalesced stores
     mbar_wait(bar_vfree, (n_kv - 1) & 1);

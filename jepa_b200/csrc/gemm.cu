@@ -89,7 +89,9 @@ VJ_DEVINL float gelu_grad_fast(float x) {
   return fmaf(x, pdf, cdf);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+// EPI is a compile-time epilogue kind so that e.g. the plain / GELU kernels carry none of the aux-tile code
+// (and registers) of the residual / dGELU ones.
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
@@ -242,9 +244,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         sts32f(bias_u32 + 4 * i, (p.bias != nullptr && split == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f);
       named_bar_sync(1, kEpiWarps * 32);
 
+      const int row0 = m0 + q * 32;
+      // aux tile (residual / pos-embed / pre-activation) prefetch: the coalesced global loads of chunk c+1 are in
+      // flight while chunk c is being processed; chunk 0 is issued before we even wait for the accumulator.
+      const bool use_aux = (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU);
+      const bool a128 = p.aux_f32 != 0;
+      const int cshift = a128 ? 3 : 2;
+      const int cpr = 1 << cshift;           // 16B chunks per aux row (shifts, not runtime integer divisions)
+      const int rows_per_it = 32 >> cshift;
+      const int ach = lane & (cpr - 1);
+      const int arow = lane >> cshift;
+      uint4 axv[(EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 1];
+      auto aux_issue = [&](int c) {
+        const int col0 = g * COLS_PER_WARP + c * 32;
+#pragma unroll
+        for (int it = 0; it < ((EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 0); ++it) {
+          if (it < cpr) {
+            const int r = it * rows_per_it + arow;
+            const int grow = row0 + r;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (grow < p.M) {
+              long long srow = grow;
+              if (p.aux_rowmap != nullptr) srow = p.aux_rowmap[grow];
+              else if (p.aux_period > 0) srow = grow % p.aux_period;
+              const long long ecol = n0 + col0 + ach * (a128 ? 4 : 8);
+              if (ecol < p.N) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) + (srow * p.ldaux + ecol) * (a128 ? 4 : 2);
+                val = __ldg(reinterpret_cast<const uint4*>(src));
+              }
+            }
+            axv[it] = val;
+          }
+        }
+      };
+      if (use_aux) aux_issue(0);
+
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row0 = m0 + q * 32;
 
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
@@ -274,31 +310,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
 
-        if (p.epi == VJ_EPI_ADD || p.epi == VJ_EPI_DGELU) {
-          // coalesced global -> smem of the aux tile (32 rows x 32 cols), then each thread picks up its own row
-          const bool a128 = p.aux_f32 != 0;
+        if (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) {
+          // the prefetched aux tile (32 rows x 32 cols) goes through smem so each thread can pick up its own row
           const uint32_t abuf = (a128 || OUT_F32) ? bufA : bufB;   // bf16 aux next to a bf16 D tile: no TMA ever reads bufB
           if (a128 || OUT_F32) wait_prev_store();
-          const int cpr = a128 ? 8 : 4;  // 16B chunks per row
-          const int rows_per_it = 32 / cpr;
-          const int ch = lane % cpr;
-          for (int it = 0; it < cpr; ++it) {
-            const int r = it * rows_per_it + lane / cpr;
-            const int grow = row0 + r;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (grow < p.M) {
-              long long srow = grow;
-              if (p.aux_rowmap != nullptr) srow = p.aux_rowmap[grow];
-              else if (p.aux_period > 0) srow = grow % p.aux_period;
-              const long long ecol = n0 + col0 + ch * (a128 ? 4 : 8);
-              if (ecol < p.N) {
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) +
-                                     (srow * p.ldaux + ecol) * (a128 ? 4 : 2);
-                val = *reinterpret_cast<const uint4*>(src);
-              }
-            }
-            sts128(abuf + swz_off(r, ch, a128), val);
-          }
+#pragma unroll
+          for (int it = 0; it < ((EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 0); ++it)
+            if (it < cpr) sts128(abuf + swz_off(it * rows_per_it + arow, ach, a128), axv[it]);
+          if (c + 1 < NCHUNK) aux_issue(c + 1);
           __syncwarp();
           float a[32];
           if (a128) {
@@ -318,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           __syncwarp();
-          if (p.epi == VJ_EPI_ADD) {
+          if (EPI == VJ_EPI_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += a[j];
           } else {
@@ -327,7 +346,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         bool two_stores = false;
-        if (p.epi == VJ_EPI_GELU) {
+        if (EPI == VJ_EPI_GELU) {
           if (p.has_auxout && !OUT_F32) {
             // pre-activation (needed by the backward) leaves through bufB, gelu(pre) through bufA, one bulk group
             wait_prev_store();
@@ -386,11 +405,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD,
                        const CUtensorMap& tX, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, EPI>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -405,22 +424,25 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
 }
 
 template <int BN>
-static int dispatch_major(int a_mn, int b_mn, int out_f32, const CUtensorMap& tA,
-                          const CUtensorMap& tB, const CUtensorMap& tD, const CUtensorMap& tX,
-                          const GemmParams& p, cudaStream_t s) {
+static int dispatch_major(int a_mn, int b_mn, int out_f32, int epi, const CUtensorMap& tA, const CUtensorMap& tB,
+                          const CUtensorMap& tD, const CUtensorMap& tX, const GemmParams& p, cudaStream_t s) {
+  // instantiated combinations = what the V-JEPA step needs (forward Linear: K/K; dgrad: K/MN; wgrad: MN/MN fp32)
   if (!a_mn && !b_mn) {
-    return out_f32 ? launch_gemm<BN, false, false, true>(tA, tB, tD, tX, p, s)
-                   : launch_gemm<BN, false, false, false>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
+                                           : launch_gemm<BN, false, false, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_ADD) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_ADD>(tA, tB, tD, tX, p, s)
+                                          : launch_gemm<BN, false, false, false, VJ_EPI_ADD>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_GELU && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_GELU>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+  } else if (!a_mn && b_mn) {
+    if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
+                                           : launch_gemm<BN, false, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32) return launch_gemm<BN, false, true, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+  } else if (a_mn && b_mn) {
+    if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, true, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
+                                           : launch_gemm<BN, true, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
   }
-  if (!a_mn && b_mn) {
-    return out_f32 ? launch_gemm<BN, false, true, true>(tA, tB, tD, tX, p, s)
-                   : launch_gemm<BN, false, true, false>(tA, tB, tD, tX, p, s);
-  }
-  if (a_mn && b_mn) {
-    return out_f32 ? launch_gemm<BN, true, true, true>(tA, tB, tD, tX, p, s)
-                   : launch_gemm<BN, true, true, false>(tA, tB, tD, tX, p, s);
-  }
-  set_error("vj_gemm: A MN-major with B K-major is not instantiated");
+  set_error("vj_gemm: combination a_mn=%d b_mn=%d d_f32=%d epi=%d is not instantiated", a_mn, b_mn, out_f32, epi);
   return -1;
 }
 
@@ -490,8 +512,8 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
     tX = tD;
   }
   switch (BN) {
-    case 256: return dispatch_major<256>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
-    case 128: return dispatch_major<128>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
-    default:  return dispatch_major<64>(a_mn, b_mn, d_f32, tA, tB, tD, tX, p, stream);
+    case 256: return dispatch_major<256>(a_mn, b_mn, d_f32, epi, tA, tB, tD, tX, p, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, d_f32, epi, tA, tB, tD, tX, p, stream);
+    default:  return dispatch_major<64>(a_mn, b_mn, d_f32, epi, tA, tB, tD, tX, p, stream);
   }
 }

@@ -166,6 +166,7 @@ def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch):
     H, hd, hdp = spec.heads, spec.hd, spec.hdp
     gv = lambda name: store.grad_view(gflat, name)
     delta_ws = _empty((H * T,), F32, dev)
+    dq_acc_ws = _empty((T, W), F32, dev) if hdp <= 32 else None   # enables the fused dQ path of the attention bwd
     for w, s in zip(reversed(weights), reversed(saved)):
         pre = w.prefix
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(ln2)))
@@ -182,7 +183,7 @@ def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch):
         dattn = _empty((T, W), BF16, dev)
         K.gemm(dx_mid, w.proj_w, dattn, b_mn=True)
         dqkv = _empty((T, 3 * W), BF16, dev)
-        K.attn_bwd(s.qkv, s.attn, dattn, s.lse, delta_ws, dqkv, cu, nseq, max_len, H, hdp, spec.scale)
+        K.attn_bwd(s.qkv, s.attn, dattn, s.lse, delta_ws, dqkv, cu, nseq, max_len, H, hdp, spec.scale, dq_acc_ws)
         dln1 = _empty((T, D), BF16, dev)
         K.gemm(dqkv, w.qkv_w, dln1, b_mn=True)
         if not spec.padded:

@@ -74,13 +74,15 @@ def attn_fwd(qkv, out, lse2, cu_seqlens, nseq, max_len, H, HD, scale):
     return out
 
 
-def attn_bwd(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, HD, scale):
+def attn_bwd(qkv, out, dout, lse2, delta_ws, dqkv, cu_seqlens, nseq, max_len, H, HD, scale, dq_acc_ws=None):
     for t, n in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         _chk(t, BF16, n)
     _chk(lse2, F32, "lse2"); _chk(delta_ws, F32, "delta_ws")
     T = qkv.shape[0]
-    _lib.call("vj_attn_bwd", _p(qkv), _p(out), _p(dout), _p(lse2), _p(delta_ws), _p(dqkv), _p(cu_seqlens), nseq,
-              max_len, H, HD, T, float(scale), _s())
+    if dq_acc_ws is not None:
+        _chk(dq_acc_ws, F32, "dq_acc_ws")
+    _lib.call("vj_attn_bwd", _p(qkv), _p(out), _p(dout), _p(lse2), _p(delta_ws), _p(dqkv), _p(dq_acc_ws), _p(cu_seqlens),
+              nseq, max_len, H, HD, T, float(scale), _s())
     return dqkv
 
 

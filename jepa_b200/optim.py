@@ -54,7 +54,7 @@ class FlatAdamW(torch.optim.Optimizer):
         gid = torch.full((store.total // 64,), 255, dtype=torch.uint8)
         for gi, p in members:
             off, n, _ = store.offsets[p._vj_name]
-            gid[off // 64:(off + n + 63) // 64] = gi
+            gid[off // 64:(off + n + 63) // 64] = gi if p.requires_grad else 255   # frozen (pos_embed): untouched
         m = torch.zeros(store.total, dtype=torch.float32, device=dev)
         v = torch.zeros(store.total, dtype=torch.float32, device=dev)
         step = torch.zeros((), dtype=torch.float32)

@@ -47,7 +47,7 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
   for (size_t i = 0; i < qkv.size(); ++i) hq[i] = __float2bfloat16(qkv[i]);
   for (size_t i = 0; i < dO.size(); ++i) hdo[i] = __float2bfloat16(dO[i]);
   void *dq, *dout, *ddo, *ddqkv;
-  float *dlse, *ddelta;
+  float *dlse, *ddelta, *ddqacc;
   int* dcu;
   CK(cudaMalloc(&dq, hq.size() * 2));
   CK(cudaMalloc(&dout, (size_t)T * D * 2));
@@ -55,6 +55,7 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
   CK(cudaMalloc(&ddqkv, hq.size() * 2));
   CK(cudaMalloc(&dlse, (size_t)H * T * 4));
   CK(cudaMalloc(&ddelta, (size_t)H * T * 4));
+  CK(cudaMalloc(&ddqacc, (size_t)T * D * 4));
   CK(cudaMalloc(&dcu, (nseq + 1) * 4));
   CK(cudaMemcpy(dq, hq.data(), hq.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ddo, hdo.data(), hdo.size() * 2, cudaMemcpyHostToDevice));
@@ -66,7 +67,7 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("FAIL attn_fwd kernel error %s\n", cudaGetErrorString(e)); exit(3); }
   if (do_bwd) {
-    rc = vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, dcu, nseq, max_len, H, HD, T, scale, nullptr);
+    rc = vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, ddqacc, dcu, nseq, max_len, H, HD, T, scale, nullptr);
     if (rc) { printf("FAIL attn_bwd rc=%d %s\n", rc, vj_last_error_string()); return 1; }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("FAIL attn_bwd kernel error %s\n", cudaGetErrorString(e)); exit(3); }
@@ -155,10 +156,11 @@ static void perf(int H, int HD, int nseq, int L, bool bwd) {
   const int T = nseq * L, W = 3 * H * HD, D = H * HD;
   std::vector<int> cu(nseq + 1);
   for (int i = 0; i <= nseq; ++i) cu[i] = i * L;
-  void *dq, *dout, *ddo, *ddqkv; float *dlse, *ddelta; int* dcu;
+  void *dq, *dout, *ddo, *ddqkv; float *dlse, *ddelta, *ddqacc; int* dcu;
   CK(cudaMalloc(&dq, (size_t)T * W * 2)); CK(cudaMalloc(&dout, (size_t)T * D * 2));
   CK(cudaMalloc(&ddo, (size_t)T * D * 2)); CK(cudaMalloc(&ddqkv, (size_t)T * W * 2));
   CK(cudaMalloc(&dlse, (size_t)H * T * 4)); CK(cudaMalloc(&ddelta, (size_t)H * T * 4));
+  CK(cudaMalloc(&ddqacc, (size_t)T * D * 4));
   CK(cudaMalloc(&dcu, (nseq + 1) * 4));
   CK(cudaMemset(dq, 0x3C, (size_t)T * W * 2)); CK(cudaMemset(ddo, 0x3C, (size_t)T * D * 2));
   CK(cudaMemcpy(dcu, cu.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice));
@@ -166,14 +168,14 @@ static void perf(int H, int HD, int nseq, int L, bool bwd) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 2; ++i) {
     vj_attn_fwd(dq, dout, dlse, dcu, nseq, L, H, HD, T, scale, nullptr);
-    if (bwd) vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, dcu, nseq, L, H, HD, T, scale, nullptr);
+    if (bwd) vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, ddqacc, dcu, nseq, L, H, HD, T, scale, nullptr);
   }
   CK(cudaDeviceSynchronize());
   const int iters = 5;
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i) {
     if (!bwd) vj_attn_fwd(dq, dout, dlse, dcu, nseq, L, H, HD, T, scale, nullptr);
-    else vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, dcu, nseq, L, H, HD, T, scale, nullptr);
+    else vj_attn_bwd(dq, dout, ddo, dlse, ddelta, ddqkv, ddqacc, dcu, nseq, L, H, HD, T, scale, nullptr);
   }
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());

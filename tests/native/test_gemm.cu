@@ -224,23 +224,32 @@ int main(int argc, char** argv) {
     if (only && !strstr(c.name, only)) continue;
     fails += run_case(c, verbose);
   }
-  if (!only || strstr("perf", only)) {
-    perf(50176, 4096, 1024, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_gelu_target");
-    perf(50176, 1024, 4096, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_add_target");
-    perf(50176, 3072, 1024, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_target");
-    perf(13056, 4096, 1024, 0, 1, 0, VJ_EPI_NONE, 1, "dgrad_ctx");
-    perf(4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 1, "wgrad_ctx_fc1");
-    perf(1024, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 4, "wgrad_ctx_proj_split4");
-    perf(76032, 1536, 384, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_pred");
-    perf(76032, 1536, 384, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_pred");
-    perf(76032, 384, 512, 0, 0, 0, VJ_EPI_ADD, 1, "proj_pred");
-    perf(76032, 384, 1536, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_pred");
-    perf(76032, 1536, 384, 0, 1, 0, VJ_EPI_DGELU, 1, "fc2_dgrad_pred");
-    perf(76032, 384, 1536, 0, 1, 0, VJ_EPI_NONE, 1, "fc1_dgrad_pred");
-    perf(1536, 384, 76032, 1, 1, 1, VJ_EPI_NONE, 4, "fc1_wgrad_pred_split4");
-    perf(384, 1536, 76032, 1, 1, 1, VJ_EPI_NONE, 8, "fc2_wgrad_pred_split8");
-    perf(13056, 1024, 1024, 0, 0, 0, VJ_EPI_ADD, 1, "proj_ctx");
-    perf(13056, 4096, 1024, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_ctx");
+  if (!only || !strncmp(only, "perf", 4)) {
+    const char* sub = (only && only[4] == ':') ? only + 5 : nullptr;   // "perf:<substring>" runs matching cases only
+    struct P { int M, N, K, a, b, f32, epi, split; const char* name; };
+    const P cases[] = {
+        {50176, 4096, 1024, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_gelu_target"},
+        {50176, 1024, 4096, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_add_target"},
+        {50176, 3072, 1024, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_target"},
+        {13056, 4096, 1024, 0, 1, 0, VJ_EPI_NONE, 1, "dgrad_ctx"},
+        {4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 1, "wgrad_ctx_fc1"},
+        {1024, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 4, "wgrad_ctx_proj_split4"},
+        {76032, 1536, 384, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_pred"},
+        {76032, 1536, 384, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_pred"},
+        {76032, 384, 512, 0, 0, 0, VJ_EPI_ADD, 1, "proj_pred"},
+        {76032, 384, 1536, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_pred"},
+        {76032, 1536, 384, 0, 1, 0, VJ_EPI_DGELU, 1, "fc2_dgrad_pred"},
+        {76032, 384, 1536, 0, 1, 0, VJ_EPI_NONE, 1, "fc1_dgrad_pred"},
+        {76032, 1536, 384, 0, 1, 0, VJ_EPI_NONE, 1, "kmn_none_pred_1536x384"},
+        {76032, 1536, 384, 0, 0, 0, VJ_EPI_DGELU, 1, "kk_dgelu_pred_1536x384"},
+        {13056, 4096, 1024, 0, 1, 0, VJ_EPI_DGELU, 1, "fc2_dgrad_ctx"},
+        {1536, 384, 76032, 1, 1, 1, VJ_EPI_NONE, 4, "fc1_wgrad_pred_split4"},
+        {384, 1536, 76032, 1, 1, 1, VJ_EPI_NONE, 8, "fc2_wgrad_pred_split8"},
+        {13056, 1024, 1024, 0, 0, 0, VJ_EPI_ADD, 1, "proj_ctx"},
+        {13056, 4096, 1024, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_ctx"},
+    };
+    for (const P& c : cases)
+      if (!sub || strstr(c.name, sub)) perf(c.M, c.N, c.K, c.a, c.b, c.f32, c.epi, c.split, c.name);
   }
   printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL PASSED", fails);
   return fails ? 1 : 0;

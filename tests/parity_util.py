@@ -121,9 +121,10 @@ def rel_l2(a, b):
 
 # tolerances (north_star: "within a stated fp tolerance"): bf16-operand / fp32-accumulate kernels against
 # the fp32 oracle, 12+12 layer networks.
-TOL_ACT = 3e-2      # rel-L2 on encoder / predictor / target outputs
-TOL_GRAD = 6e-2     # rel-L2 per parameter gradient
-TOL_LOSS = 5e-3     # absolute, loss ~ 0.9
+# (measured on B200, round 1: worst activation rel-L2 0.006, worst gradient rel-L2 0.013, loss diff < 1e-3)
+TOL_ACT = 2e-2      # rel-L2 on encoder / predictor / target outputs
+TOL_GRAD = 3e-2     # rel-L2 per parameter gradient
+TOL_LOSS = 3e-3     # absolute, loss ~ 0.9
 
 
 def compare_step(got, ref, verbose=False, tol_act=TOL_ACT, tol_grad=TOL_GRAD, tol_loss=TOL_LOSS):

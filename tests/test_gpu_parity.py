@@ -204,8 +204,15 @@ def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
     scale = hd ** -0.5
     Kn.attn_fwd(qkv_d, out, lse, cu, len(lens), max(lens), H, hdp, scale)
     dqkv = torch.empty_like(qkv_d)
+    # hd <= 32 exercises the fused dQ path (TMA reduce-add of per-key-tile partials), the others the two-kernel path
+    ws = torch.empty(T, H * hdp, device=dev) if hdp <= 32 else None
     Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dqkv, cu,
-                len(lens), max(lens), H, hdp, scale)
+                len(lens), max(lens), H, hdp, scale, dq_acc_ws=ws)
+    if ws is not None:   # and both paths agree
+        dq2 = torch.empty_like(qkv_d)
+        Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dq2,
+                    cu, len(lens), max(lens), H, hdp, scale)
+        close_bf16(dqkv, dq2.float().cpu(), atol=2e-2, rtol=2e-2)
     out_c, dq_c = out.float().cpu().view(T, H, hdp), dqkv.float().cpu().view(T, 3, H, hdp)
     if hdp > hd:  # padded lanes stay exactly zero end to end
         assert float(out_c[..., hd:].abs().max()) == 0 and float(dq_c[..., hd:].abs().max()) == 0
