@@ -28,6 +28,9 @@ extern "C" {
 #define VJ_EPI_GELU 1  /* D = gelu_erf(alpha*acc + bias); aux_out (bf16, optional) = pre-activation */
 #define VJ_EPI_ADD 2   /* D = alpha*acc + bias + aux[rowmap(r), c]   (residual / pos-embed) */
 #define VJ_EPI_DGELU 3 /* D = (alpha*acc + bias) * gelu_erf'(aux[r, c])                     */
+#define VJ_EPI_MUL 4   /* D = (alpha*acc + bias) * aux[r, c]                                */
+#define VJ_EPI_GELU_GRAD 5 /* like GELU, but aux_out (bf16) = gelu_erf'(pre-activation): the fc2 dgrad then
+                              only needs VJ_EPI_MUL (one erf per element per step instead of two)      */
 
 const char* vj_last_error_string(void);
 int vj_version(void);

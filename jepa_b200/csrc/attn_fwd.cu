@@ -178,30 +178,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       const int valid = min(128, len - j * 128);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      // ---- S_j -> registers (single TMEM pass), then hand the S columns back to the MMA warp
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tmem_S + lane_addr + 0, s0);
-      tmem_ld32(tmem_S + lane_addr + 32, s1);
-      tmem_ld32(tmem_S + lane_addr + 64, s2);
-      tmem_ld32(tmem_S + lane_addr + 96, s3);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree);
-      // ---- row max (tail columns of the last block masked out)
+      // ---- S_j -> registers.  Columns 0..95 stay in registers; the last 32 are only scanned for the row max
+      // here and re-read from TMEM right before their exponentials: 128 live score registers + temporaries do not
+      // fit the 168-register budget of 2 CTAs/SM, and a spill costs an L2 round trip (L1 is carved out to smem).
+      uint32_t s0[32], s1[32], s2[32];
       float mx = -INFINITY;
-      if (valid == 128) {
+      {
+        uint32_t t3[32];
+        tmem_ld32(tmem_S + lane_addr + 0, s0);
+        tmem_ld32(tmem_S + lane_addr + 32, s1);
+        tmem_ld32(tmem_S + lane_addr + 64, s2);
+        tmem_ld32(tmem_S + lane_addr + 96, t3);
+        tmem_wait_ld();
+        if (valid == 128) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          mx = fmaxf(fmaxf(mx, __uint_as_float(s0[i])),
-                     fmaxf(__uint_as_float(s1[i]), fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i]))));
-      } else {
+          for (int i = 0; i < 32; ++i)
+            mx = fmaxf(fmaxf(mx, __uint_as_float(s0[i])),
+                       fmaxf(__uint_as_float(s1[i]), fmaxf(__uint_as_float(s2[i]), __uint_as_float(t3[i]))));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
-          if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
-          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
-          if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(s3[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
+            if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
+            if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(s2[i]));
+            if (96 + i < valid) mx = fmaxf(mx, __uint_as_float(t3[i]));
+          }
         }
       }
       // ---- lazy rescale: only move the reference max when it would overflow the 2^8 head-room
@@ -227,18 +228,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       }
       const float moff = m_ref * p.scale_log2;
       // ---- p = 2^(s*scale - m), packed to bf16 pairs; the single P tile is free once PV_{j-1} retired
-      uint32_t p0[16], p1[16], p2[16], p3[16];
-      if (valid == 128) {
-        exp_pack32<true>(s0, 0, valid, p.scale_log2, moff, l, p0);
-        exp_pack32<true>(s1, 32, valid, p.scale_log2, moff, l, p1);
-        exp_pack32<true>(s2, 64, valid, p.scale_log2, moff, l, p2);
-        exp_pack32<true>(s3, 96, valid, p.scale_log2, moff, l, p3);
-      } else {
-        exp_pack32<false>(s0, 0, valid, p.scale_log2, moff, l, p0);
-        exp_pack32<false>(s1, 32, valid, p.scale_log2, moff, l, p1);
-        exp_pack32<false>(s2, 64, valid, p.scale_log2, moff, l, p2);
-        exp_pack32<false>(s3, 96, valid, p.scale_log2, moff, l, p3);
-      }
+      // the single P tile is free once PV_{j-1} retired (long done by now); each 32-column group is exponentiated,
+      // packed and stored right away so only 16 packed registers are live at a time (no spills in this loop).
       if (j > 0) mbar_wait(bar_vfree, (j - 1) & 1);
       auto put = [&](const uint32_t (&pk)[16], int g0) {
 #pragma unroll
@@ -248,7 +239,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
                  make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
         }
       };
-      put(p0, 0); put(p1, 4); put(p2, 8); put(p3, 12);
+      auto reload_last = [&]() {   // columns 96..127 again (into s0, dead by now), then S_j is handed back to the MMA warp
+        tmem_ld32(tmem_S + lane_addr + 96, s0);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree);
+      };
+      {
+        uint32_t pk[16];
+        if (valid == 128) {
+          exp_pack32<true>(s0, 0, valid, p.scale_log2, moff, l, pk); put(pk, 0);
+          exp_pack32<true>(s1, 32, valid, p.scale_log2, moff, l, pk); put(pk, 4);
+          exp_pack32<true>(s2, 64, valid, p.scale_log2, moff, l, pk); put(pk, 8);
+          reload_last(); exp_pack32<true>(s0, 96, valid, p.scale_log2, moff, l, pk); put(pk, 12);
+        } else {
+          exp_pack32<false>(s0, 0, valid, p.scale_log2, moff, l, pk); put(pk, 0);
+          exp_pack32<false>(s1, 32, valid, p.scale_log2, moff, l, pk); put(pk, 4);
+          exp_pack32<false>(s2, 64, valid, p.scale_log2, moff, l, pk); put(pk, 8);
+          reload_last(); exp_pack32<false>(s0, 96, valid, p.scale_log2, moff, l, pk); put(pk, 12);
+        }
+      }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();

@@ -91,7 +91,7 @@ VJ_DEVINL float gelu_grad_fast(float x) {
 
 // EPI is a compile-time epilogue kind so that e.g. the plain / GELU kernels carry none of the aux-tile code
 // (and registers) of the residual / dGELU ones.
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
@@ -247,19 +247,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row0 = m0 + q * 32;
       // aux tile (residual / pos-embed / pre-activation) prefetch: the coalesced global loads of chunk c+1 are in
       // flight while chunk c is being processed; chunk 0 is issued before we even wait for the accumulator.
-      const bool use_aux = (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU);
-      const bool a128 = p.aux_f32 != 0;
+      constexpr bool kUsesAux = (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU || EPI == VJ_EPI_MUL);
+      const bool use_aux = kUsesAux;
+      constexpr bool a128 = AUX32;           // aux element type is compile-time: spills here cost an L2 round trip each
       const int cshift = a128 ? 3 : 2;
       const int cpr = 1 << cshift;           // 16B chunks per aux row (shifts, not runtime integer divisions)
       const int rows_per_it = 32 >> cshift;
       const int ach = lane & (cpr - 1);
       const int arow = lane >> cshift;
-      uint4 axv[(EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 1];
+      constexpr int kAuxIt = kUsesAux ? (AUX32 ? 8 : 4) : 0;
+      uint4 axv[kAuxIt > 0 ? kAuxIt : 1];
       auto aux_issue = [&](int c) {
         const int col0 = g * COLS_PER_WARP + c * 32;
 #pragma unroll
-        for (int it = 0; it < ((EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 0); ++it) {
-          if (it < cpr) {
+        for (int it = 0; it < kAuxIt; ++it) {
+          {
             const int r = it * rows_per_it + arow;
             const int grow = row0 + r;
             uint4 val = make_uint4(0, 0, 0, 0);
@@ -310,59 +312,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
 
-        if (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) {
+        if (kUsesAux) {
           // the prefetched aux tile (32 rows x 32 cols) goes through smem so each thread can pick up its own row
           const uint32_t abuf = (a128 || OUT_F32) ? bufA : bufB;   // bf16 aux next to a bf16 D tile: no TMA ever reads bufB
           if (a128 || OUT_F32) wait_prev_store();
 #pragma unroll
-          for (int it = 0; it < ((EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU) ? 8 : 0); ++it)
-            if (it < cpr) sts128(abuf + swz_off(it * rows_per_it + arow, ach, a128), axv[it]);
+          for (int it = 0; it < kAuxIt; ++it)
+            sts128(abuf + swz_off(it * rows_per_it + arow, ach, a128), axv[it]);
           if (c + 1 < NCHUNK) aux_issue(c + 1);
           __syncwarp();
-          float a[32];
+          // each thread streams its own row back out of smem straight into the accumulator registers
+          auto apply = [&](float& acc_v, float aux_v) {
+            if (EPI == VJ_EPI_ADD) acc_v += aux_v;
+            else if (EPI == VJ_EPI_MUL) acc_v *= aux_v;
+            else acc_v *= gelu_grad_fast(aux_v);
+          };
           if (a128) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 x = lds128f(abuf + swz_off(lane, j, true));
-              a[4 * j] = x.x; a[4 * j + 1] = x.y; a[4 * j + 2] = x.z; a[4 * j + 3] = x.w;
+              apply(f[4 * j], x.x); apply(f[4 * j + 1], x.y); apply(f[4 * j + 2], x.z); apply(f[4 * j + 3], x.w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 x = lds128(abuf + swz_off(lane, j, false));
-              a[8 * j] = bf16_lo(x.x); a[8 * j + 1] = bf16_hi(x.x);
-              a[8 * j + 2] = bf16_lo(x.y); a[8 * j + 3] = bf16_hi(x.y);
-              a[8 * j + 4] = bf16_lo(x.z); a[8 * j + 5] = bf16_hi(x.z);
-              a[8 * j + 6] = bf16_lo(x.w); a[8 * j + 7] = bf16_hi(x.w);
+              apply(f[8 * j], bf16_lo(x.x)); apply(f[8 * j + 1], bf16_hi(x.x));
+              apply(f[8 * j + 2], bf16_lo(x.y)); apply(f[8 * j + 3], bf16_hi(x.y));
+              apply(f[8 * j + 4], bf16_lo(x.z)); apply(f[8 * j + 5], bf16_hi(x.z));
+              apply(f[8 * j + 6], bf16_lo(x.w)); apply(f[8 * j + 7], bf16_hi(x.w));
             }
           }
           __syncwarp();
-          if (EPI == VJ_EPI_ADD) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += a[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= gelu_grad_fast(a[j]);
-          }
         }
         bool two_stores = false;
-        if (EPI == VJ_EPI_GELU) {
-          if (p.has_auxout && !OUT_F32) {
-            // pre-activation (needed by the backward) leaves through bufB, gelu(pre) through bufA, one bulk group
-            wait_prev_store();
+        if (EPI == VJ_EPI_GELU || EPI == VJ_EPI_GELU_GRAD) {
+          // second output (needed by the backward) leaves through bufB, gelu(pre) through bufA, one bulk group:
+          //   VJ_EPI_GELU      : aux_out = pre-activation
+          //   VJ_EPI_GELU_GRAD : aux_out = gelu'(pre) = Phi(pre) + pre * pdf(pre)  (shares the erf with gelu itself, so
+          //                      the backward's epilogue is a plain multiply instead of a second erf / exp evaluation)
+          const bool second = p.has_auxout && !OUT_F32;
+          if (second) wait_prev_store();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 4; ++j) {
+            float d[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x = f[8 * j + e];
+              const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
+              if (EPI == VJ_EPI_GELU_GRAD) d[e] = fmaf(x, 0.39894228040143268f * __expf(-0.5f * x * x), cdf);
+              else d[e] = x;
+              f[8 * j + e] = x * cdf;
+            }
+            if (second) {
               uint4 o;
-              o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
+              o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
               sts128(bufB + swz_off(lane, j, false), o);
             }
-            two_stores = true;
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+          two_stores = second;
         }
 
         wait_prev_store();
@@ -405,11 +414,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32 = false>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD,
                        const CUtensorMap& tX, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, EPI>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, EPI, AUX32>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -430,14 +439,19 @@ static int dispatch_major(int a_mn, int b_mn, int out_f32, int epi, const CUtens
   if (!a_mn && !b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, false, false, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_ADD) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_ADD>(tA, tB, tD, tX, p, s)
-                                          : launch_gemm<BN, false, false, false, VJ_EPI_ADD>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_ADD) {
+      if (p.aux_f32) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_ADD, true>(tA, tB, tD, tX, p, s)
+                                    : launch_gemm<BN, false, false, false, VJ_EPI_ADD, true>(tA, tB, tD, tX, p, s);
+      if (!out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_ADD, false>(tA, tB, tD, tX, p, s);
+    }
     if (epi == VJ_EPI_GELU && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_GELU>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_DGELU && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_GELU_GRAD && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_GELU_GRAD>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, false, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
   } else if (!a_mn && b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, false, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_DGELU && !out_f32) return launch_gemm<BN, false, true, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, true, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_MUL && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, true, false, VJ_EPI_MUL>(tA, tB, tD, tX, p, s);
   } else if (a_mn && b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, true, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, true, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
@@ -463,9 +477,9 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                "vj_gemm: operands must be 16-byte aligned");
-  VJ_CHECK_ARG(epi >= VJ_EPI_NONE && epi <= VJ_EPI_DGELU, "vj_gemm: bad epilogue %d", epi);
+  VJ_CHECK_ARG(epi >= VJ_EPI_NONE && epi <= VJ_EPI_GELU_GRAD, "vj_gemm: bad epilogue %d", epi);
   VJ_CHECK_ARG(!(accumulate || split_k > 1) || d_f32, "vj_gemm: accumulate/split-K needs fp32 D");
-  if (epi == VJ_EPI_ADD || epi == VJ_EPI_DGELU) {
+  if (epi == VJ_EPI_ADD || epi == VJ_EPI_DGELU || epi == VJ_EPI_MUL) {
     VJ_CHECK_ARG(aux != nullptr, "vj_gemm: epilogue %d needs aux", epi);
     VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldaux % (aux_f32 ? 4 : 8) == 0,
                  "vj_gemm: aux misaligned");
@@ -485,7 +499,7 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.bias = bias;
   p.epi = epi;
   p.aux = aux; p.ldaux = ldaux; p.aux_f32 = aux_f32; p.aux_rowmap = aux_rowmap; p.aux_period = aux_period;
-  p.has_auxout = (epi == VJ_EPI_GELU && aux_out != nullptr) ? 1 : 0;
+  p.has_auxout = ((epi == VJ_EPI_GELU || epi == VJ_EPI_GELU_GRAD) && aux_out != nullptr) ? 1 : 0;
   p.reduce_add = (accumulate || p.split_k > 1) ? 1 : 0;
   p.alpha = alpha;
   p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;

@@ -35,7 +35,7 @@ VJ_DEVINL void st8(void* base, long long off, const float (&v)[8]) {
 }
 
 template <int NV, bool IN_F32, bool OUT_F32>
-__global__ void __launch_bounds__(256, NV <= 4 ? 4 : 2)
+__global__ void __launch_bounds__(256, NV <= 2 ? 4 : (NV <= 4 ? 3 : 1))
 ln_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
               const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int T, int D,
               float eps) {
@@ -92,7 +92,9 @@ ln_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __r
 // its storage format between the two passes; dgamma/dbeta partial sums live in per-warp shared-memory
 // slices (no atomics, no persistent registers), reduced per block into [gridDim.x, D] partials.
 template <int NV, bool X_F32>
-__global__ void __launch_bounds__(256, 3)
+// (register caps chosen so nothing spills: with ~220 KB of the SM given to shared memory L1 is tiny and every
+// local-memory access is an L2 round trip)
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const void* __restrict__ dres,
               void* __restrict__ dx, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int T, int D) {
@@ -190,16 +192,19 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, 
   }
 }
 
-// out_a[c] += sum_r a[r,c]; out_b[c] += sum_r b[r,c]: 32 columns x 8 row groups per block, coalesced rows
+// out_a[c] += sum_r a[r,c]; out_b[c] += sum_r b[r,c].  grid = (C/32, row chunks): 32 columns x 8 row groups per
+// block, coalesced 128-byte row segments, one atomicAdd per (column, row chunk).
 __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                              float* __restrict__ out_a, float* __restrict__ out_b,
-                                                             int R, int C) {
+                                                             int R, int C, int rows_per_block) {
   __shared__ float sm[2][8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rg = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
   float sa = 0.f, sb = 0.f;
   if (col < C) {
-    for (int r = rg; r < R; r += 8) {
+    for (int r = r0 + rg; r < r1; r += 8) {
       sa += a[(long long)r * C + col];
       sb += b[(long long)r * C + col];
     }
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += sm[which][i][cc];
-      (which ? out_b : out_a)[c] += s;
+      atomicAdd(&(which ? out_b : out_a)[c], s);
     }
   }
 }
@@ -311,7 +316,11 @@ extern "C" int vj_layernorm_bwd(const void* dy, const void* x, int x_f32, const 
   VJ_LN_DISPATCH(D, VJ_CALL);
 #undef VJ_CALL
   VJ_CUDA(cudaGetLastError());
-  partial_reduce_kernel<<<(D + 31) / 32, 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, D);
+  {
+    const int rows_per_block = 64;
+    dim3 rgrid((D + 31) / 32, (grid + rows_per_block - 1) / rows_per_block);
+    partial_reduce_kernel<<<rgrid, 256, 0, s>>>(pg, pb, dgamma, dbeta, grid, D, rows_per_block);
+  }
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(2);
   return 0;

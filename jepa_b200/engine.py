@@ -140,7 +140,8 @@ def blocks_forward(spec, weights, x, seq, save):
         ln2 = _empty((T, D), BF16, dev) if save else ln
         K.layernorm_fwd(x_mid, ln2, w.n2w, w.n2b, LN_EPS, s.mean2 if save else None, s.rstd2 if save else None)
         h = _empty((T, Hd), BF16, dev) if save else None
-        K.gemm(ln2, w.fc1_w, g, bias=w.fc1_b, epi=K.EPI_GELU, aux_out=h)
+        # training: keep gelu'(pre-activation) (bf16) instead of the pre-activation itself, computed in the same epilogue
+        K.gemm(ln2, w.fc1_w, g, bias=w.fc1_b, epi=K.EPI_GELU_GRAD if save else K.EPI_GELU, aux_out=h)
         x_out = _empty((T, D), BF16, dev)
         K.gemm(g, w.fc2_w, x_out, bias=w.fc2_b, epi=K.EPI_ADD, aux=x_mid)
         if save:
@@ -171,7 +172,7 @@ def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch):
         pre = w.prefix
         # ---- MLP: x_out = x_mid + fc2(gelu(fc1(ln2)))
         dh = _empty((T, Hd), BF16, dev)
-        K.gemm(dx, w.fc2_w, dh, b_mn=True, epi=K.EPI_DGELU, aux=s.h)             # (dx W2) * gelu'(h)
+        K.gemm(dx, w.fc2_w, dh, b_mn=True, epi=K.EPI_MUL, aux=s.h)               # (dx W2) * gelu'(h), s.h holds gelu'(h)
         _wgrad(dx, s.g, gv(pre + "mlp.fc2.weight"), gv(pre + "mlp.fc2.bias"), T)
         dln2 = _empty((T, D), BF16, dev)
         K.gemm(dh, w.fc1_w, dln2, b_mn=True)

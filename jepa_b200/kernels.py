@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-EPI_NONE, EPI_GELU, EPI_ADD, EPI_DGELU = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_ADD, EPI_DGELU, EPI_MUL, EPI_GELU_GRAD = 0, 1, 2, 3, 4, 5
 BF16, F32 = torch.bfloat16, torch.float32
 
 

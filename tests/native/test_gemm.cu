@@ -59,7 +59,7 @@ static int run_case(const Case& c, bool verbose) {
   if (c.use_rowmap) aux_rows = 97;
   std::vector<int> rowmap(M);
   for (int m = 0; m < M; ++m) rowmap[m] = (m * 7 + 3) % 97;
-  const bool need_aux = c.epi == VJ_EPI_ADD || c.epi == VJ_EPI_DGELU;
+  const bool need_aux = c.epi == VJ_EPI_ADD || c.epi == VJ_EPI_DGELU || c.epi == VJ_EPI_MUL;
   aux.resize((size_t)aux_rows * N);
   for (auto& v : aux) v = c.aux_f32 ? frand() : bf(frand());
   D0.resize((size_t)M * N);
@@ -135,6 +135,8 @@ static int run_case(const Case& c, bool verbose) {
       double pre = v;
       int arow = c.use_rowmap ? rowmap[m] : (c.aux_period > 0 ? m % c.aux_period : m);
       if (c.epi == VJ_EPI_GELU) v = gelu_ref(v);
+      else if (c.epi == VJ_EPI_GELU_GRAD) { v = gelu_ref(v); pre = dgelu_ref(pre); }
+      else if (c.epi == VJ_EPI_MUL) v *= aux[(size_t)arow * N + n];
       else if (c.epi == VJ_EPI_ADD) v += aux[(size_t)arow * N + n];
       else if (c.epi == VJ_EPI_DGELU) v *= dgelu_ref(aux[(size_t)arow * N + n]);
       if (c.accumulate) v += D0[(size_t)m * N + n];
@@ -181,12 +183,12 @@ static void perf(int M, int N, int K, int a_mn, int b_mn, int d_f32, int epi, in
   const int iters = 10;
   for (int i = 0; i < 3; ++i)
     vj_gemm(dA, a_mn ? M : K, a_mn, dB, b_mn ? N : K, b_mn, dD, N, d_f32, M, N, K, dBias, 1.f, epi, dAux, N, 0,
-            nullptr, 0, nullptr, 0, split_k, 0, nullptr);
+            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, 0, nullptr);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i)
     vj_gemm(dA, a_mn ? M : K, a_mn, dB, b_mn ? N : K, b_mn, dD, N, d_f32, M, N, K, dBias, 1.f, epi, dAux, N, 0,
-            nullptr, 0, nullptr, 0, split_k, 0, nullptr);
+            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, 0, nullptr);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
@@ -217,6 +219,10 @@ int main(int argc, char** argv) {
       {"add_f32_period", 300, 256, 192, 0, 0, 0, VJ_EPI_ADD, 1, 0, 100, 0, 1, 0, 1},
       {"add_f32_rowmap", 300, 256, 192, 0, 0, 0, VJ_EPI_ADD, 1, 1, 0, 0, 1, 0, 1},
       {"dgelu_dgrad", 300, 512, 256, 0, 1, 0, VJ_EPI_DGELU, 0, 0, 0, 0, 1, 0, 0},
+      {"mul_dgrad", 300, 512, 256, 0, 1, 0, VJ_EPI_MUL, 0, 0, 0, 0, 1, 0, 0},
+      {"mul_dgrad_bn128", 300, 384, 256, 0, 1, 0, VJ_EPI_MUL, 0, 0, 0, 0, 1, 0, 0},
+      {"gelu_grad_auxout", 300, 768, 192, 0, 0, 0, VJ_EPI_GELU_GRAD, 0, 0, 0, 1, 1, 0, 1},
+      {"gelu_grad_auxout_bn128", 300, 384, 192, 0, 0, 0, VJ_EPI_GELU_GRAD, 0, 0, 0, 1, 1, 0, 1},
       {"kk_big", 4000, 1024, 1024, 0, 0, 0, VJ_EPI_NONE, 0, 0, 0, 0, 1, 0, 1},
   };
   const char* only = argc > 1 ? argv[1] : nullptr;
@@ -239,6 +245,10 @@ int main(int argc, char** argv) {
         {76032, 384, 512, 0, 0, 0, VJ_EPI_ADD, 1, "proj_pred"},
         {76032, 384, 1536, 0, 0, 0, VJ_EPI_ADD, 1, "fc2_pred"},
         {76032, 1536, 384, 0, 1, 0, VJ_EPI_DGELU, 1, "fc2_dgrad_pred"},
+        {76032, 1536, 384, 0, 1, 0, VJ_EPI_MUL, 1, "fc2_dgrad_pred_mul"},
+        {13056, 4096, 1024, 0, 1, 0, VJ_EPI_MUL, 1, "fc2_dgrad_ctx_mul"},
+        {76032, 1536, 384, 0, 0, 0, VJ_EPI_GELU_GRAD, 1, "fc1_pred_gelugrad"},
+        {13056, 4096, 1024, 0, 0, 0, VJ_EPI_GELU_GRAD, 1, "fc1_ctx_gelugrad"},
         {76032, 384, 1536, 0, 1, 0, VJ_EPI_NONE, 1, "fc1_dgrad_pred"},
         {76032, 1536, 384, 0, 1, 0, VJ_EPI_NONE, 1, "kmn_none_pred_1536x384"},
         {76032, 1536, 384, 0, 0, 0, VJ_EPI_DGELU, 1, "kk_dgelu_pred_1536x384"},
