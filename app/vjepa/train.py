@@ -22,7 +22,7 @@ import time
 import numpy as np
 import torch
 import torch.multiprocessing as mp
-from torch.nn.parallel import DistributedDataParallel
+from src.utils.distributed import DistributedDataParallel   # flat-buffer gradient exchange, torch DDP surface
 
 from app.vjepa.transforms import make_transforms
 from app.vjepa.utils import init_opt, init_video_model, load_checkpoint

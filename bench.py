@@ -152,7 +152,10 @@ def build_training_state(cfg_name, device, world, rank):
         ref_lr=OPT["lr"], final_lr=OPT["final_lr"], iterations_per_epoch=OPT["ipe"], warmup=OPT["warmup"],
         num_epochs=OPT["epochs"], ipe_scale=OPT["ipe_scale"], mixed_precision=True)
     if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
+        if os.environ.get("VJ_TORCH_DDP"):   # A/B: torch's reducer buckets instead of the flat-buffer exchange
+            from torch.nn.parallel import DistributedDataParallel as DDP
+        else:
+            from jepa_b200.distributed import DistributedDataParallel as DDP
         encoder = DDP(encoder, static_graph=True)
         predictor = DDP(predictor, static_graph=True)
         target = DDP(target)

@@ -87,3 +87,102 @@ class AllReduce(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grads):
         return grads
+
+
+# -------------------------------------------------------------------------------------------------
+# Data-parallel gradient exchange over the flat gradient buffers
+# -------------------------------------------------------------------------------------------------
+_pending = []           # NCCL work handles of all-reduces issued during the current backward pass
+_callback_queued = [False]
+
+
+def _wait_pending():
+    """Make the compute stream wait for every outstanding gradient all-reduce (stream-side wait, no host sync)."""
+    _callback_queued[0] = False
+    while _pending:
+        _pending.pop().wait()
+
+
+class FlatGradSync:
+    """Bucketed, asynchronous averaging all-reduce of one FlatParamStore gradient buffer.
+
+    The backward of a network writes its flat fp32 gradient buffer from the END towards the START (parameters are
+    laid out in registration order, backward visits them in reverse), so "everything at or above offset `lo` is final"
+    is all the engine has to report (`ready_down_to`).  Each time at least `bucket_bytes` have become final that suffix
+    slice is all-reduced in place on NCCL's stream while the compute stream goes on with the earlier layers; the
+    compute stream waits for the handles once, in an end-of-backward callback.  No bucket copies: the optimiser reads
+    the same buffer (torch DDP's role in app/vjepa/train.py:193-195 of the reference).
+    """
+
+    def __init__(self, process_group=None, bucket_bytes=96 << 20):
+        self.group = process_group
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.gflat = None
+        self.hi = 0         # everything in [hi, total) has been handed to NCCL already
+        self.lo = 0         # everything in [lo, hi) is final but not yet sent
+        self.n_calls = 0    # all-reduces issued for the current buffer (tests / launch accounting)
+
+    def begin(self, gflat):
+        self.gflat = gflat
+        self.hi = self.lo = gflat.numel()
+        self.n_calls = 0
+
+    def _issue(self, lo, hi):
+        if hi <= lo:
+            return
+        world = dist.get_world_size(self.group)
+        chunk = self.gflat[lo:hi]
+        if dist.get_backend(self.group) == 'nccl':
+            work = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:  # gloo (CPU tests): no AVG
+            chunk.div_(world)
+            work = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.n_calls += 1
+        _pending.append(work)
+        if not _callback_queued[0]:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(_wait_pending)
+                _callback_queued[0] = True
+            except RuntimeError:    # not inside a backward pass: caller must use finish(wait=True)
+                pass
+
+    def ready_down_to(self, lo):
+        """Gradients at flat offsets >= lo are final."""
+        if self.gflat is None or lo >= self.lo:
+            return
+        self.lo = lo
+        if self.hi - self.lo >= self.bucket_elems:
+            self._issue(self.lo, self.hi)
+            self.hi = self.lo
+
+    def finish(self, wait=False):
+        """The whole buffer is final: send what is left; optionally wait right here instead of at end of backward."""
+        if self.gflat is None:
+            return
+        self._issue(0, self.hi)
+        self.hi = self.lo = 0
+        self.gflat = None
+        if wait or not _callback_queued[0]:
+            _wait_pending()
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """Data-parallel wrapper with torch DDP's surface (`.module`, `module.`-prefixed state dict, forward passthrough,
+    parameters broadcast from rank 0 at construction) whose gradient exchange is FlatGradSync on the flat gradient
+    buffers instead of reducer buckets.  Frozen modules (the target encoder) only get the broadcast."""
+
+    def __init__(self, module, device_ids=None, static_graph=False, process_group=None, bucket_cap_mb=96, **_ignored):
+        super().__init__()
+        self.module = module
+        self.process_group = process_group
+        if _active():
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, 0, group=process_group)
+            if any(p.requires_grad for p in module.parameters()):
+                for m in module.modules():
+                    if hasattr(m, '_store') and hasattr(m, '_spec'):
+                        m._vj_grad_sync = FlatGradSync(process_group, bucket_cap_mb << 20)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

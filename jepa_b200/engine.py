@@ -159,8 +159,17 @@ def _wgrad(dy, act, grad_out, bias_grad, tokens):
         K.colsum(dy, bias_grad)
 
 
-def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch):
-    """Backward through the Block stack.  dx [T, dim] bf16 is d(loss)/d(stack output); returns d/d(input)."""
+def _sync_begin(mod, gflat):
+    """Data-parallel gradient exchange (jepa_b200.distributed.FlatGradSync) attached to this network, or None."""
+    sync = getattr(mod, "_vj_grad_sync", None)
+    if sync is not None:
+        sync.begin(gflat)
+    return sync
+
+
+def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch, sync=None):
+    """Backward through the Block stack.  dx [T, dim] bf16 is d(loss)/d(stack output); returns d/d(input).
+    `sync`: told after every block that the flat gradients from that block's first parameter upwards are final."""
     cu, nseq, max_len, T = seq
     dev = dx.device
     D, Hd, W = spec.dim, spec.hidden, spec.inner
@@ -206,6 +215,8 @@ def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch):
         K.layernorm_bwd(dln1, s.x_in, w.n1w, s.mean1, s.rstd1, dx_mid, dx_in, gv(pre + "norm1.weight"),
                         gv(pre + "norm1.bias"))
         dx = dx_in
+        if sync is not None:
+            sync.ready_down_to(store.offsets[pre + "norm1.weight"][0])
     return dx
 
 
@@ -285,9 +296,12 @@ def encoder_backward(mod, sv, dout):
     dx = _empty((T, D), BF16, dev)
     K.layernorm_bwd(dout.contiguous(), sv.x_final, store.f32("norm.weight"), sv.mean, sv.rstd, None, dx,
                     gv("norm.weight"), gv("norm.bias"))
-    dx = blocks_backward(spec, sv.weights, sv.blocks, dx, sv.seq, store, gflat, mod._scratch)
+    sync = _sync_begin(mod, gflat)
+    dx = blocks_backward(spec, sv.weights, sv.blocks, dx, sv.seq, store, gflat, mod._scratch, sync)
     P = sv.patches.shape[1]
     _wgrad(dx, sv.patches, gv("patch_embed.proj.weight").view(D, P), gv("patch_embed.proj.bias"), T)
+    if sync is not None:
+        sync.finish()
     return gflat
 
 
@@ -386,7 +400,8 @@ def predictor_backward(mod, sv, dout):
     dx = _empty((T, Dp), BF16, dev)
     K.layernorm_bwd(dln, sv.x_final, store.f32("predictor_norm.weight"), sv.mean, sv.rstd, None, dx,
                     gv("predictor_norm.weight"), gv("predictor_norm.bias"))
-    dx = blocks_backward(spec, sv.weights, sv.blocks, dx, sv.seq, store, gflat, mod._scratch)
+    sync = _sync_begin(mod, gflat)
+    dx = blocks_backward(spec, sv.weights, sv.blocks, dx, sv.seq, store, gflat, mod._scratch, sync)
     # input assembly: context rows -> d(embed out); target rows -> d(mask token)
     Tc = sum(B * k for k in Ke)
     demb = _empty((Tc, Dp), BF16, dev)
@@ -400,4 +415,6 @@ def predictor_backward(mod, sv, dout):
     dz = _empty((Tc, Denc), BF16, dev)
     K.gemm(demb, store.bf16("predictor_embed.weight"), dz, b_mn=True)
     _wgrad(demb, sv.z_cat, gv("predictor_embed.weight"), gv("predictor_embed.bias"), Tc)
+    if sync is not None:
+        sync.finish()       # overlaps with the context encoder's backward; waited for at the end of the backward pass
     return dz, gflat

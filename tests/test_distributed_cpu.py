@@ -56,6 +56,91 @@ def test_two_rank_gloo_collectives():
     assert res[0][5] == res[1][5] == [[4.5] * 4] * 2  # mean over ranks of 3 * (rank + 1)
 
 
+class _FakeStore:
+    """offset table of a 3-block toy network in a flat buffer (the layout jepa_b200.params.FlatParamStore produces)."""
+    def __init__(self):
+        self.offsets, off = {}, 0
+        for name, n in [("embed.weight", 40), ("pos", 10)] + [(f"blocks.{i}.{k}", 25) for i in range(3)
+                                                            for k in ("norm1.weight", "fc.weight")] + [("norm.weight", 7)]:
+            self.offsets[name] = (off, n, (n,))
+            off += n
+        self.total = off
+
+
+class _FlatBackward(torch.autograd.Function):
+    """Writes a flat gradient buffer back to front the way engine.encoder_backward does and drives FlatGradSync."""
+    @staticmethod
+    def forward(ctx, x, store, sync, gflat, fill):
+        ctx.args = (store, sync, gflat, fill)
+        return x.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        store, sync, gflat, fill = ctx.args
+        sync.begin(gflat)
+        o, n, _ = store.offsets["norm.weight"]
+        gflat[o:o + n] = fill
+        for i in (2, 1, 0):
+            lo = store.offsets[f"blocks.{i}.norm1.weight"][0]
+            gflat[lo:lo + 50] = fill * (i + 1)
+            sync.ready_down_to(lo)
+        gflat[:40] = fill * 10     # embed; "pos" stays zero (frozen)
+        sync.finish()
+        return g.expand(4), None, None, None, None
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    from src.utils.distributed import DistributedDataParallel, FlatGradSync, init_distributed
+    init_distributed(port=port, rank_and_world_size=(rank, world))
+    store = _FakeStore()
+    out = []
+    for bucket_bytes in (4, 60 * 4, 1 << 30):     # a bucket per block / two blocks per bucket / one bucket at the end
+        sync = FlatGradSync(bucket_bytes=bucket_bytes)
+        gflat = torch.zeros(store.total)
+        x = torch.ones(4, requires_grad=True)
+        _FlatBackward.apply(x, store, sync, gflat, float(rank + 1)).backward()
+        out.append((sync.n_calls, gflat.tolist()))
+    # outside a backward pass: finish(wait=True)
+    sync = FlatGradSync()
+    g = torch.full((8,), float(rank))
+    sync.begin(g)
+    sync.finish(wait=True)
+    # wrapper: rank-0 parameters everywhere, `module.` state-dict prefix, forward passthrough
+    torch.manual_seed(rank)
+    ddp = DistributedDataParallel(torch.nn.Linear(3, 2), static_graph=True)
+    q.put((rank, out, g.tolist(), ddp.module.weight.tolist(), sorted(ddp.state_dict()),
+           list(ddp(torch.ones(1, 3)).shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_sync_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    store = _FakeStore()
+    want = torch.zeros(store.total)
+    want[store.offsets["norm.weight"][0]:] = 1.5
+    for i in range(3):
+        lo = store.offsets[f"blocks.{i}.norm1.weight"][0]
+        want[lo:lo + 50] = 1.5 * (i + 1)
+    want[:40] = 15.0
+    for (n0, g0), (n1, g1), n_expected in zip(res[0][1], res[1][1], (4, 2, 1)):
+        assert n0 == n1 == n_expected                   # bucket schedule identical on every rank (collective order)
+        assert g0 == g1 == want.tolist()                # averaged in place, frozen slot untouched
+    assert res[0][2] == res[1][2] == [0.5] * 8
+    assert res[0][3] == res[1][3]
+    assert res[0][4] == ["module.bias", "module.weight"] and res[0][5] == [1, 2]
+
+
 def test_init_distributed_without_slurm_returns_single_process(monkeypatch):
     from src.utils.distributed import init_distributed
     monkeypatch.delenv("SLURM_NTASKS", raising=False)
