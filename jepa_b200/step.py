@@ -9,13 +9,15 @@ from . import engine
 from . import kernels as K
 from .models import _common_base, _token_views, MultiMaskWrapper, PredictorMultiMaskWrapper
 
+from .distributed import DistributedDataParallel as _FlatDDP  # noqa: E402
+
 TARGET_LN_EPS = 1e-5  # F.layer_norm default eps, app/vjepa/train.py:426
 
 
 def unwrap(module):
     """Strip DistributedDataParallel / multi-mask wrappers down to the backbone."""
     m = module
-    if hasattr(m, "module") and isinstance(m, torch.nn.parallel.DistributedDataParallel):
+    if hasattr(m, "module") and isinstance(m, (torch.nn.parallel.DistributedDataParallel, _FlatDDP)):
         m = m.module
     if isinstance(m, (MultiMaskWrapper, PredictorMultiMaskWrapper)):
         m = m.backbone

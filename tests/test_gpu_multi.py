@@ -34,6 +34,14 @@ def _step(enc, pred, tgt, clips, me, mp):
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception:       # surface the failure in the parent instead of letting it wait for the queue
+        import traceback
+        q.put((rank, "error", traceback.format_exc()))
+
+
+def _worker_body(rank, world, port, q):
     import torch.distributed as dist
     from common import C1, synth_clips
     from parity_util import build_states, c1_masks
@@ -51,7 +59,7 @@ def _worker(rank, world, port, q):
     enc, pred, tgt = MultiMaskWrapper(enc).to(device), PredictorMultiMaskWrapper(pred).to(device), MultiMaskWrapper(tgt).to(device)
     for p in tgt.parameters():
         p.requires_grad = False
-    B = 4
+    B = C1["batch"]
     clips = synth_clips(B, C1["num_frames"], C1["crop_size"], C1["crop_size"], seed=100 + rank).to(device)
     me, mp = c1_masks(B)
     me, mp = [m.to(device) for m in me], [m.to(device) for m in mp]
@@ -98,7 +106,12 @@ def test_flat_grad_sync_nccl_two_gpus():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
+    res = []
+    for _ in range(world):
+        r = q.get(timeout=240)
+        assert r[1] != "error", r[2]
+        res.append(r)
+    res.sort()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
