@@ -24,6 +24,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;
   int H, T;
   float scale, scale_log2;
+  int dbg;   // VJ_DBG_ATTN ablation bits (timing experiments only; results are wrong when non-zero)
 };
 
 template <int HD>
@@ -44,6 +45,9 @@ struct BwdCfg {
   static constexpr int DKV_TMEM = (128 + (CAN_FUSE_DQ ? 3 : 2) * HD) <= 256 ? 256 : 512;
   static constexpr int DQ_TMEM = (128 + HD) <= 256 ? 256 : 512;
 };
+
+__device__ long long g_attn_ts[16 * 64];   // TEMP: timeline instrumentation
+#define TS(slot) do { if (ts_on && lane == 0) g_attn_ts[i * 16 + (slot)] = clock64(); } while (0)
 
 VJ_DEVINL void named_bar_sync_attn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -112,8 +116,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // FUSE_DQ: the CTA also forms dQ_i (partial over this key tile) = dS_i K  - A operand = the dS^T tile read M-major,
 // B = the K tile read MN-major - and reduce-adds it (TMA, fp32) into a global accumulator, which makes the
 // separate dQ kernel (a second exp / S / dP recomputation) unnecessary.
+constexpr int kDkvThreads = 64 + 8 * 32;   // TMA warp, MMA warp, 8 softmax warps
+
 template <int HD, bool FUSE_DQ>
-__global__ void __launch_bounds__(kAttnThreads, HD <= 64 ? 2 : 1)
+__global__ void __launch_bounds__(kDkvThreads, HD <= 64 ? 2 : 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
   using C = AttnCfg<HD>;
@@ -132,12 +138,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   const uint32_t bar_kv = smem_u32(bars + 0), bar_qdo = smem_u32(bars + 1), bar_qdofree = smem_u32(bars + 3);
   const uint32_t bar_s = smem_u32(bars + 5), bar_p = smem_u32(bars + 6), bar_pvdone = smem_u32(bars + 7);
   const uint32_t bar_dp = smem_u32(bars + 8), bar_ds = smem_u32(bars + 9), bar_psfree = smem_u32(bars + 10);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const uint32_t bar_stat = smem_u32(bars + 11), bar_statfree = smem_u32(bars + 13);   // [2] each
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool ts_on = (p.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 8 && (warp == 1 || warp == 2);
   if (threadIdx.x == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
-    for (int st = 0; st < 2; ++st) { mbar_init(bar_qdo + 8 * st, 1); mbar_init(bar_qdofree + 8 * st, 1); }
-    mbar_init(bar_p, 4); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 4);
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(bar_qdo + 8 * st, 1); mbar_init(bar_qdofree + 8 * st, 1);
+      mbar_init(bar_stat + 8 * st, 1); mbar_init(bar_statfree + 8 * st, 8);
+    }
+    mbar_init(bar_p, 8); mbar_init(bar_pvdone, 1); mbar_init(bar_dp, 1); mbar_init(bar_ds, 8);
     mbar_init(bar_psfree, 1);
     fence_mbar_init();
   }
@@ -161,18 +172,44 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         tma_load_2d(sK + b * C::BOX_BYTES, &tmQKV, bar_kv, HHD + head * HD + b * C::BOX_INNER, row_begin + kv0);
         tma_load_2d(sV + b * C::BOX_BYTES, &tmQKV, bar_kv, 2 * HHD + head * HD + b * C::BOX_INNER, row_begin + kv0);
       }
-      for (int i = 0; i < n_q; ++i) {
-        const int st = i % ST;
-        const uint32_t u = uint32_t(i / ST) & 1;
-        mbar_wait(bar_qdofree + 8 * st, u ^ 1);
-        mbar_expect_tx(bar_qdo + 8 * st, 2 * C::TILE_BYTES);
+    }
+    const uint32_t stats_w = smem_u32(smem + B::STAT_OFF);
+    auto load_qdo = [&](int i) {   // lane 0: Q_i / dO_i tiles into stage i % ST
+      const int st = i % ST;
+      mbar_wait(bar_qdofree + 8 * st, (uint32_t(i / ST) & 1) ^ 1);
+      mbar_expect_tx(bar_qdo + 8 * st, 2 * C::TILE_BYTES);
 #pragma unroll
-        for (int b = 0; b < C::NBOX; ++b) {
-          tma_load_2d(sQ + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_qdo + 8 * st,
-                      head * HD + b * C::BOX_INNER, row_begin + i * 128);
-          tma_load_2d(sDO + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmDO, bar_qdo + 8 * st,
-                      head * HD + b * C::BOX_INNER, row_begin + i * 128);
-        }
+      for (int b = 0; b < C::NBOX; ++b) {
+        tma_load_2d(sQ + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmQKV, bar_qdo + 8 * st,
+                    head * HD + b * C::BOX_INNER, row_begin + i * 128);
+        tma_load_2d(sDO + st * B::STAGE_BYTES + b * C::BOX_BYTES, &tmDO, bar_qdo + 8 * st,
+                    head * HD + b * C::BOX_INNER, row_begin + i * 128);
+      }
+    };
+    if (lane == 0) load_qdo(0);
+    for (int i = 0; i < n_q; ++i) {
+      // per-query-row softmax statistics of tile i -> smem ring of 2 (keeps the global-load latency off the
+      // softmax warps' chain).  +inf LSE for rows past the sequence end -> ex2(s - inf) = 0: no predicates needed.
+      const int sb = i & 1;
+      if (i >= 2) mbar_wait(bar_statfree + 8 * sb, uint32_t((i >> 1) - 1) & 1);
+      float lv[4], dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {   // all 8 loads in flight before the first store
+        const int qrow = i * 128 + k * 32 + lane;
+        const bool ok = qrow < len;
+        const long long g = (long long)head * p.T + row_begin + qrow;
+        lv[k] = ok ? p.lse2[g] : INFINITY;
+        dv[k] = ok ? p.delta[g] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sts32f(stats_w + sb * 1024 + 4 * (k * 32 + lane), lv[k]);
+        sts32f(stats_w + sb * 1024 + 512 + 4 * (k * 32 + lane), dv[k]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_stat + 8 * sb);
+        if (i + 1 < n_q) load_qdo(i + 1);   // may block on the stage being released; the statistics are already out
       }
     }
     __syncwarp();
@@ -181,36 +218,46 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       constexpr uint32_t idesc_128 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_hd = make_idesc_bf16(128, HD, 0, 1);
       mbar_wait(bar_kv, 0);
-      for (int i = 0; i < n_q; ++i) {
-        const uint32_t ph = i & 1;
-        const int st = i % ST;
-        const uint32_t sQi = sQ + st * B::STAGE_BYTES, sDOi = sDO + st * B::STAGE_BYTES;
-        mbar_wait(bar_qdo + 8 * st, uint32_t(i / ST) & 1);
+      // With a double-buffered Q / dO stream (ST == 2) the MMAs are ordered so that the softmax warps never wait
+      // for more than two short MMAs: S^T_{i+1} goes out right after dS_i is published (before the long dK / dQ
+      // MMAs of tile i), and dP^T_i before dV_i.
+      auto issue_S = [&](int i) {
+        const uint32_t sQi = sQ + (i % ST) * B::STAGE_BYTES;
+        mbar_wait(bar_qdo + 8 * (i % ST), uint32_t(i / ST) & 1);
         tc_fence_after();
-        // S^T = K Q_i^T
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
           umma_f16(tmem_ST, kmajor_desc<HD>(sK, kk), kmajor_desc<HD>(sQi, kk), idesc_128, kk > 0);
         umma_commit(bar_s);
+      };
+      for (int i = 0; i < n_q; ++i) {
+        const uint32_t ph = i & 1;
+        const int st = i % ST;
+        const uint32_t sQi = sQ + st * B::STAGE_BYTES, sDOi = sDO + st * B::STAGE_BYTES;
+        if (ST == 1 || i == 0) issue_S(i);    // S^T = K Q_i^T
         mbar_wait(bar_p, ph);
+        TS(9);
         tc_fence_after();
-        // dV += P^T dO_i
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
-        umma_commit(bar_pvdone);
         // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
           umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
         umma_commit(bar_dp);
+        // dV += P^T dO_i
+#pragma unroll
+        for (int kk = 0; kk < ((p.dbg & 8) ? 1 : 8); ++kk)
+          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
+        umma_commit(bar_pvdone);
+        TS(10);
         mbar_wait(bar_ds, ph);
+        TS(11);
         tc_fence_after();
+        if (ST == 2 && i + 1 < n_q) issue_S(i + 1);
         // dK += dS^T Q_i
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < ((p.dbg & 8) ? 1 : 8); ++kk)
           umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
-        if (FUSE_DQ) {
+        if (FUSE_DQ && !(p.dbg & 2)) {
           // dQ_i partial [q, hd] = dS_i [q, kv] K [kv, hd]: A = dS^T tile as M-major (q contiguous), B = K MN-major
           constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);
 #pragma unroll
@@ -219,18 +266,24 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         umma_commit(bar_qdofree + 8 * st);
         umma_commit(bar_psfree);
+        TS(12);
       }
     }
     __syncwarp();
   } else {
+    // 8 softmax warps: warp (qd, half) owns key rows qd*32.. (its TMEM lane quarter) x query columns half*64..+64.
+    // Two warps per scheduler per CTA (four with the co-resident CTA) hide the ld / MUFU / barrier latencies that a
+    // single warp per scheduler exposes.
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = qd * 32 + lane;  // key row inside the tile
-    const int tid = threadIdx.x - 64;
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     const uint32_t stats = smem_u32(smem + B::STAT_OFF);
     const uint32_t ps = sPS;
-    const uint32_t dqs = smem_u32(smem + B::DQS_OFF) + (warp - 2) * 4096;
+    const uint32_t dqs = smem_u32(smem + B::DQS_OFF) + qd * 4096;   // half-0 warps drain the dQ partials
     const uint32_t kvmask = (!FUSE_DQ || kv0 + r < len) ? 0xFFFFFFFFu : 0u;
+    const bool kv_partial = FUSE_DQ && kv0 + 128 > len;
+    const int col0 = half * 64;
     auto drain_dq = [&](int qi) {   // dQ partial of query tile qi (lanes = query rows) -> global fp32 accumulator
       uint32_t v[32];
       tmem_ld32(tmem_dQ + lane_addr, v);
@@ -243,112 +296,114 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(p.dbg & 1)) {
         tma_reduce_add_2d(&tmDQ, dqs, head * HD, row_begin + qi * 128 + qd * 32);
         tma_commit_group();
       }
     };
     for (int i = 0; i < n_q; ++i) {
       const uint32_t ph = i & 1;
-      const uint32_t lse_s = stats + (i & 1) * 1024;
+      const uint32_t lse_s = stats + (i & 1) * 1024 + 4 * col0;
       const uint32_t del_s = lse_s + 512;
-      {
-        const int qrow = i * 128 + tid;
-        const bool ok = qrow < len;
-        // +inf for rows past the sequence end -> ex2(s - inf) = 0: invalid queries drop out without predicates
-        sts32f(lse_s + 4 * tid, ok ? p.lse2[(long long)head * p.T + row_begin + qrow] : INFINITY);
-        sts32f(del_s + 4 * tid, ok ? p.delta[(long long)head * p.T + row_begin + qrow] : 0.f);
-      }
-      named_bar_sync_attn(1, 128);
-      // the P/dS tile is free once the previous iteration's dK MMA retired
-      if (i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
+      mbar_wait(bar_stat + 8 * (i & 1), uint32_t(i >> 1) & 1);
+      TS(0);
       mbar_wait(bar_s, ph);
+      TS(1);
       tc_fence_after();
-      uint32_t pk[64];
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tmem_ST + lane_addr + c * 32, v);
+        tmem_ld32(tmem_ST + lane_addr + col0 + c * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 L = lds128f(lse_s + 4 * (c * 32 + e));
-          const float a0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x));
-          const float a1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y));
-          const float a2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z));
-          const float a3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w));
-          // fused dQ sums over key rows, so rows past the sequence end must carry P = dS = 0 (kvmask);
-          // for dK / dV alone they are merely never stored
-          pk[c * 16 + e / 2] = pack_bf16x2(a0, a1) & kvmask;
-          pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3) & kvmask;
+          float a0 = fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x);
+          float a1 = fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y);
+          float a2 = fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z);
+          float a3 = fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w);
+          if (!(p.dbg & 4)) { a0 = ex2_approx(a0); a1 = ex2_approx(a1); a2 = ex2_approx(a2); a3 = ex2_approx(a3); }
+          pk[c * 16 + e / 2] = pack_bf16x2(a0, a1);
+          pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3);
         }
+        // fused dQ sums over key rows, so rows past the sequence end must carry P = dS = 0; for dK / dV alone they
+        // are merely never stored.  Only the last key tile of a sequence can have such rows.
+        if (kv_partial) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[c * 16 + e] &= kvmask;
+        }
+        // the P/dS tile is free once the previous iteration's dK (and dQ) MMAs retired; by then the dQ partial of
+        // tile i-1 is complete as well (drained below)
+        if (c == 0) TS(2);
+        if (c == 0 && i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
+        if (c == 0) TS(3);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          ptile_store(ps, r, c * 4 + g,
+          if (!(p.dbg & 16))
+          ptile_store(ps, r, half * 8 + c * 4 + g,
                       make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]));
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      // S^T_i was issued after the dQ MMA of iteration i-1, so that partial is complete: drain it now, off the
-      // MMA warp's critical path (it is busy with dV / dP^T).
-      if (FUSE_DQ && i > 0) drain_dq(i - 1);
+      TS(4);
+      // bar_psfree(i-1) was observed above, so the dQ partial of tile i-1 is complete: drain it now, off the MMA
+      // warp's critical path (it is busy with dP^T / dV).
+      if (FUSE_DQ && half == 0 && i > 0 && !(p.dbg & 2)) { tc_fence_after(); drain_dq(i - 1); }
+      TS(5);
       mbar_wait(bar_dp, ph);
-      mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
+      TS(6);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tmem_ST + lane_addr + c * 32, v);
+        tmem_ld32(tmem_ST + lane_addr + col0 + c * 32, v);
         tmem_wait_ld();
         uint32_t ds[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 Dl = lds128f(del_s + 4 * (c * 32 + e));
-          const uint32_t pp0 = pk[c * 16 + e / 2], pp1 = pk[c * 16 + e / 2 + 1];
-          ds[e / 2] = pack_bf16x2(bf16_lo(pp0) * (__uint_as_float(v[e]) - Dl.x),
-                                  bf16_hi(pp0) * (__uint_as_float(v[e + 1]) - Dl.y));
-          ds[e / 2 + 1] = pack_bf16x2(bf16_lo(pp1) * (__uint_as_float(v[e + 2]) - Dl.z),
-                                      bf16_hi(pp1) * (__uint_as_float(v[e + 3]) - Dl.w));
+          // dS = P o (dP - delta) in packed bf16: the factor is rounded to bf16 like P, one HMUL2 per two elements
+          ds[e / 2] = mul_bf16x2(pk[c * 16 + e / 2],
+                                 pack_bf16x2(__uint_as_float(v[e]) - Dl.x, __uint_as_float(v[e + 1]) - Dl.y));
+          ds[e / 2 + 1] = mul_bf16x2(pk[c * 16 + e / 2 + 1],
+                                     pack_bf16x2(__uint_as_float(v[e + 2]) - Dl.z, __uint_as_float(v[e + 3]) - Dl.w));
         }
+        if (c == 0) mbar_wait(bar_pvdone, ph);
+        if (c == 0) TS(7);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          ptile_store(ps, r, c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+          if (!(p.dbg & 16))
+          ptile_store(ps, r, half * 8 + c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ds);
+      if (lane == 0) { mbar_arrive(bar_ds); mbar_arrive(bar_statfree + 8 * (i & 1)); }
+      TS(8);
     }
-    // epilogue: dV, dK (x scale) -> bf16 -> dqkv[:, v / k third]
+    // epilogue: half-0 warps store dV, half-1 warps dK (x scale) -> bf16 -> dqkv[:, v / k third], 32 columns at a time
     mbar_wait(bar_psfree, (n_q - 1) & 1);
     tc_fence_after();
-    if (FUSE_DQ) drain_dq(n_q - 1);
+    if (FUSE_DQ && half == 0 && !(p.dbg & 2)) drain_dq(n_q - 1);
     const int rows_valid = max(0, min(32, len - kv0 - qd * 32));
-    const uint32_t stage = ps + (warp - 2) * (32 * HD * 2);
-    float acc[HD];
-#pragma unroll
+    const uint32_t stage = ps + (warp - 2) * 2048;
+    const uint32_t tmem_src = half == 0 ? tmem_dV : tmem_dK;
+    const float mul = half == 0 ? 1.0f : p.scale;
+    __nv_bfloat16* gbase = p.dqkv + (half == 0 ? 2 : 1) * HHD + head * HD;
+#pragma unroll 1
     for (int c = 0; c < HD / 32; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_dV + lane_addr + c * 32, v);
+      tmem_ld32(tmem_src + lane_addr + c * 32, v);
       tmem_wait_ld();
+      float acc[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) acc[c * 32 + e] = __uint_as_float(v[e]);
+      for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v[e]);
+      store_rows_bf16<32>(stage, acc, mul, lane, gbase + c * 32, 3LL * HHD, row_begin + kv0 + qd * 32, rows_valid);
     }
-    store_rows_bf16<HD>(stage, acc, 1.0f, lane, p.dqkv + 2 * HHD + head * HD, 3LL * HHD,
-                        row_begin + kv0 + qd * 32, rows_valid);
-#pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_dK + lane_addr + c * 32, v);
-      tmem_wait_ld();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) acc[c * 32 + e] = __uint_as_float(v[e]);
-    }
-    store_rows_bf16<HD>(stage, acc, p.scale, lane, p.dqkv + HHD + head * HD, 3LL * HHD,
-                        row_begin + kv0 + qd * 32, rows_valid);
-    if (FUSE_DQ && lane == 0) tma_wait_group<0>();
+    if (FUSE_DQ && half == 0 && lane == 0) tma_wait_group<0>();
     tc_fence_before();
   }
   tc_fence_before();
@@ -595,9 +650,11 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   AttnBwdParams p;
   p.cu_seqlens = cu; p.lse2 = lse2; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.H = H; p.T = T; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  static const int dbg = getenv("VJ_DBG_ATTN") ? atoi(getenv("VJ_DBG_ATTN")) : 0;
+  p.dbg = dbg;
   dim3 grid((max_len + 127) / 128, nseq, H);
   if (fuse) {
-    kdkv_fused<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
+    kdkv_fused<<<grid, kDkvThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
     VJ_CUDA(cudaGetLastError());
     long long n4 = (long long)T * H * HD / 4;
     long long g = (n4 + 255) / 256;
@@ -607,7 +664,7 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
     vj::count_launch(2);
     return 0;
   }
-  kdkv<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
+  kdkv<<<grid, kDkvThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
   kdq<<<grid, kAttnThreads, B::SMEM_BYTES, s>>>(tq, tdo, p);
@@ -617,6 +674,10 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
 }
 
 }  // namespace vj
+
+extern "C" int vj_debug_attn_ts(long long* out, int n) {   // TEMP
+  return (int)cudaMemcpyFromSymbol(out, vj::g_attn_ts, sizeof(long long) * n);
+}
 
 extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
                            void* dqkv, float* dq_acc_ws, const int* cu_seqlens, int nseq, int max_len, int H, int HD,

@@ -255,6 +255,12 @@ VJ_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// packed bf16 multiply (HMUL2.BF16): both lanes rounded to nearest even
+VJ_DEVINL uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 VJ_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 VJ_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -46,19 +46,28 @@ struct GemmParams {
   // smem-descriptor strides (bytes); overridable through VJ_DBG_* env vars while bringing the
   // kernel up on hardware.
   unsigned lbo_k, sbo_k, lbo_mn, sbo_mn;
+  int dbg;   // TEMP ablation bits (VJ_DBG_GEMM)
 };
 
-template <int BN>
+constexpr int kAuxRing = 3;          // aux tiles (32 x 32 bf16 = 2 KB) in flight per epilogue warp
+constexpr int kAuxTileBytes = 2048;
+
+// AUXRING: the epilogue reads a bf16 aux matrix (residual / saved gelu') through a per-warp ring of TMA loads; the
+// ring's smem is paid for with one or two operand stages (these GEMMs are epilogue-bound, not pipeline-depth-bound).
+template <int BN, bool AUXRING = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = AUXRING ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_OFF = EPI_OFF + kEpiWarps * kEpiBufBytes;
+  static constexpr int RING_OFF = EPI_OFF + kEpiWarps * kEpiBufBytes;
+  static constexpr int BIAS_OFF = RING_OFF + (AUXRING ? kEpiWarps * kAuxRing * kAuxTileBytes : 0);
   static constexpr int BAR_OFF = BIAS_OFF + BN * 4;
-  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;  // +1024 align slack
+  static constexpr int NBARS = 2 * STAGES + 4 + kEpiWarps * kAuxRing;
+  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;  // +1024 align slack
   static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(SMEM_BYTES <= 232448, "GEMM shared memory budget exceeded");
 };
 
 VJ_DEVINL uint32_t swz_off(int row, int chunk, bool rows128) {
@@ -91,12 +100,16 @@ VJ_DEVINL float gelu_grad_fast(float x) {
 
 // EPI is a compile-time epilogue kind so that e.g. the plain / GELU kernels carry none of the aux-tile code
 // (and registers) of the residual / dGELU ones.
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32, bool RING>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  constexpr bool kUsesAux = (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU || EPI == VJ_EPI_MUL);
+  constexpr bool kRing = RING;   // bf16 aux through the TMA ring (short-K GEMMs) or through registers (long-K: keeps
+                                 // the full operand pipeline depth, the epilogue is a small fraction there)
+  static_assert(!RING || (kUsesAux && !AUX32), "aux ring needs a bf16 aux epilogue");
+  using Cfg = GemmCfg<BN, kRing>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -104,7 +117,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* epi_base = smem + Cfg::EPI_OFF;
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBARS);
+  const uint32_t rbar_base = smem_u32(bars + 2 * STAGES + 4);   // [kEpiWarps][kAuxRing] aux-tile "full" barriers
 
   const uint32_t full0 = smem_u32(bars);
   const uint32_t empty0 = smem_u32(bars + STAGES);
@@ -123,12 +137,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, kEpiWarps);
     }
+    if (kRing)
+      for (int i = 0; i < kEpiWarps * kAuxRing; ++i) mbar_init(rbar_base + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmX);
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
@@ -231,7 +248,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int etid = threadIdx.x - 64;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr bool OUT128 = OUT_F32;  // staged rows are 128 B (fp32) or 64 B (bf16)
+    // aux ring (kRing): this warp's aux tiles are consumed in a fixed order (tile by tile, chunk by chunk), so lane 0
+    // keeps kAuxRing TMA loads in flight ahead of the consumer - across tile boundaries - and re-arms a slot as soon
+    // as it has been read.  HBM latency of the aux stream never reaches the accumulator drain.
+    const uint32_t ring_u32 = smem_u32(smem + Cfg::RING_OFF) + ew * (kAuxRing * kAuxTileBytes);
+    const uint32_t rbar0 = rbar_base + 8 * (ew * kAuxRing);
+    long long ring_w = blockIdx.x;   // tile of the next aux chunk to request
+    int ring_c = 0;                  // ... and its chunk index
+    auto ring_issue = [&](int slot) {   // lane 0 only
+      if (ring_w < total) {
+        const int split = int(ring_w / tiles);
+        const int t = int(ring_w - (long long)split * tiles);
+        const int rm0 = (t / p.tiles_n) * BM, rn0 = (t % p.tiles_n) * BN;
+        mbar_expect_tx(rbar0 + 8 * slot, kAuxTileBytes);
+        tma_load_2d(ring_u32 + slot * kAuxTileBytes, &tmX, rbar0 + 8 * slot, rn0 + g * COLS_PER_WARP + ring_c * 32,
+                    rm0 + q * 32);
+        if (++ring_c == NCHUNK) { ring_c = 0; ring_w += gridDim.x; }
+      }
+    };
+    int rslot = 0;
+    uint32_t rphase = 0;
+    if (kRing && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kAuxRing; ++i) ring_issue(i);
+    }
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int split = w / tiles;
@@ -247,15 +287,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row0 = m0 + q * 32;
       // aux tile (residual / pos-embed / pre-activation) prefetch: the coalesced global loads of chunk c+1 are in
       // flight while chunk c is being processed; chunk 0 is issued before we even wait for the accumulator.
-      constexpr bool kUsesAux = (EPI == VJ_EPI_ADD || EPI == VJ_EPI_DGELU || EPI == VJ_EPI_MUL);
-      const bool use_aux = kUsesAux;
+      const bool use_aux = kUsesAux && !kRing;
       constexpr bool a128 = AUX32;           // aux element type is compile-time: spills here cost an L2 round trip each
       const int cshift = a128 ? 3 : 2;
       const int cpr = 1 << cshift;           // 16B chunks per aux row (shifts, not runtime integer divisions)
       const int rows_per_it = 32 >> cshift;
       const int ach = lane & (cpr - 1);
       const int arow = lane >> cshift;
-      constexpr int kAuxIt = kUsesAux ? (AUX32 ? 8 : 4) : 0;
+      constexpr int kAuxIt = (kUsesAux && !kRing) ? (AUX32 ? 8 : 4) : 0;
       uint4 axv[kAuxIt > 0 ? kAuxIt : 1];
       auto aux_issue = [&](int c) {
         const int col0 = g * COLS_PER_WARP + c * 32;
@@ -270,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (p.aux_rowmap != nullptr) srow = p.aux_rowmap[grow];
               else if (p.aux_period > 0) srow = grow % p.aux_period;
               const long long ecol = n0 + col0 + ach * (a128 ? 4 : 8);
-              if (ecol < p.N) {
+              if (ecol < p.N && !(p.dbg & 2)) {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) + (srow * p.ldaux + ecol) * (a128 ? 4 : 2);
                 val = __ldg(reinterpret_cast<const uint4*>(src));
               }
@@ -297,7 +336,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), p.alpha, lds32f(bias_u32 + 4 * (col0 + j)));
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = lds128f(bias_u32 + 4 * (col0 + 4 * j));
+          f[4 * j] = fmaf(__uint_as_float(v[4 * j]), p.alpha, b4.x);
+          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), p.alpha, b4.y);
+          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), p.alpha, b4.z);
+          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), p.alpha, b4.w);
+        }
 
         // Staging: the 4 KB per-warp buffer is one fp32 tile, or two bf16 tiles (bufA = TMA-store source of D,
         // bufB = aux staging / pre-activation store source).  The wait for the previous chunk's TMA stores to
@@ -312,7 +357,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
 
-        if (kUsesAux) {
+        auto apply = [&](float& acc_v, float aux_v) {
+          if (EPI == VJ_EPI_ADD) acc_v += aux_v;
+          else if (EPI == VJ_EPI_MUL) acc_v *= aux_v;
+          else acc_v *= gelu_grad_fast(aux_v);
+        };
+        if (kRing) {
+          // aux tile of this chunk: landed by TMA (64B-swizzled like the D staging tile); each thread streams its own
+          // row straight into the accumulator registers, then lane 0 re-arms the slot with the chunk kAuxRing ahead
+          mbar_wait(rbar0 + 8 * rslot, rphase);
+          const uint32_t abuf = ring_u32 + rslot * kAuxTileBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 x = lds128(abuf + swz_off(lane, j, false));
+            apply(f[8 * j], bf16_lo(x.x)); apply(f[8 * j + 1], bf16_hi(x.x));
+            apply(f[8 * j + 2], bf16_lo(x.y)); apply(f[8 * j + 3], bf16_hi(x.y));
+            apply(f[8 * j + 4], bf16_lo(x.z)); apply(f[8 * j + 5], bf16_hi(x.z));
+            apply(f[8 * j + 6], bf16_lo(x.w)); apply(f[8 * j + 7], bf16_hi(x.w));
+          }
+          __syncwarp();
+          if (lane == 0) ring_issue(rslot);
+          if (++rslot == kAuxRing) { rslot = 0; rphase ^= 1; }
+        } else if (kUsesAux) {
           // the prefetched aux tile (32 rows x 32 cols) goes through smem so each thread can pick up its own row
           const uint32_t abuf = (a128 || OUT_F32) ? bufA : bufB;   // bf16 aux next to a bf16 D tile: no TMA ever reads bufB
           if (a128 || OUT_F32) wait_prev_store();
@@ -322,11 +388,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c + 1 < NCHUNK) aux_issue(c + 1);
           __syncwarp();
           // each thread streams its own row back out of smem straight into the accumulator registers
-          auto apply = [&](float& acc_v, float aux_v) {
-            if (EPI == VJ_EPI_ADD) acc_v += aux_v;
-            else if (EPI == VJ_EPI_MUL) acc_v *= aux_v;
-            else acc_v *= gelu_grad_fast(aux_v);
-          };
           if (a128) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -392,7 +453,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 1)) {
           if (two_stores) tma_store_2d(&tmX, bufB, n0 + col0, row0);
           if (OUT_F32 && p.reduce_add) tma_reduce_add_2d(&tmD, bufA, n0 + col0, row0);
           else tma_store_2d(&tmD, bufA, n0 + col0, row0);
@@ -414,11 +475,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32 = false>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32 = false, bool RING = false>
 static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tD,
                        const CUtensorMap& tX, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, EPI, AUX32>;
+  using Cfg = GemmCfg<BN, RING>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT_F32, EPI, AUX32, RING>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -436,22 +497,26 @@ template <int BN>
 static int dispatch_major(int a_mn, int b_mn, int out_f32, int epi, const CUtensorMap& tA, const CUtensorMap& tB,
                           const CUtensorMap& tD, const CUtensorMap& tX, const GemmParams& p, cudaStream_t s) {
   // instantiated combinations = what the V-JEPA step needs (forward Linear: K/K; dgrad: K/MN; wgrad: MN/MN fp32)
+  const bool ring = p.K <= 1024;   // bf16 aux via the TMA ring for short reductions (see gemm_kernel)
   if (!a_mn && !b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, false, false, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
     if (epi == VJ_EPI_ADD) {
       if (p.aux_f32) return out_f32 ? launch_gemm<BN, false, false, true, VJ_EPI_ADD, true>(tA, tB, tD, tX, p, s)
                                     : launch_gemm<BN, false, false, false, VJ_EPI_ADD, true>(tA, tB, tD, tX, p, s);
-      if (!out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_ADD, false>(tA, tB, tD, tX, p, s);
+      if (!out_f32) return ring ? launch_gemm<BN, false, false, false, VJ_EPI_ADD, false, true>(tA, tB, tD, tX, p, s)
+                                : launch_gemm<BN, false, false, false, VJ_EPI_ADD, false, false>(tA, tB, tD, tX, p, s);
     }
     if (epi == VJ_EPI_GELU && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_GELU>(tA, tB, tD, tX, p, s);
     if (epi == VJ_EPI_GELU_GRAD && !out_f32) return launch_gemm<BN, false, false, false, VJ_EPI_GELU_GRAD>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, false, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, false, false, VJ_EPI_DGELU, false, true>(tA, tB, tD, tX, p, s);
   } else if (!a_mn && b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, false, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, false, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, true, false, VJ_EPI_DGELU>(tA, tB, tD, tX, p, s);
-    if (epi == VJ_EPI_MUL && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, true, false, VJ_EPI_MUL>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_DGELU && !out_f32 && !p.aux_f32) return launch_gemm<BN, false, true, false, VJ_EPI_DGELU, false, true>(tA, tB, tD, tX, p, s);
+    if (epi == VJ_EPI_MUL && !out_f32 && !p.aux_f32)
+      return ring ? launch_gemm<BN, false, true, false, VJ_EPI_MUL, false, true>(tA, tB, tD, tX, p, s)
+                  : launch_gemm<BN, false, true, false, VJ_EPI_MUL, false, false>(tA, tB, tD, tX, p, s);
   } else if (a_mn && b_mn) {
     if (epi == VJ_EPI_NONE) return out_f32 ? launch_gemm<BN, true, true, true, VJ_EPI_NONE>(tA, tB, tD, tX, p, s)
                                            : launch_gemm<BN, true, true, false, VJ_EPI_NONE>(tA, tB, tD, tX, p, s);
@@ -503,6 +568,7 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.reduce_add = (accumulate || p.split_k > 1) ? 1 : 0;
   p.alpha = alpha;
   p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;
+  p.dbg = getenv("VJ_DBG_GEMM") ? atoi(getenv("VJ_DBG_GEMM")) : 0;
   if (const char* e = getenv("VJ_DBG_LBO_K")) p.lbo_k = unsigned(atoi(e));
   if (const char* e = getenv("VJ_DBG_SBO_K")) p.sbo_k = unsigned(atoi(e));
   if (const char* e = getenv("VJ_DBG_LBO_MN")) p.lbo_mn = unsigned(atoi(e));
@@ -521,6 +587,12 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   if (p.has_auxout) {
     VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(aux_out) & 15) == 0 && ldauxout % 8 == 0, "vj_gemm: aux_out misaligned");
     rc = make_tmap_2d(&tX, aux_out, 0, N, M, ldauxout * 2, 32, 32, 2);
+    if (rc) return rc;
+  } else if ((epi == VJ_EPI_ADD || epi == VJ_EPI_DGELU || epi == VJ_EPI_MUL) && !aux_f32) {
+    // bf16 aux [M, N]: read by the epilogue warps through TMA (same 32 x 32 / 64B-swizzle box as the D tile)
+    VJ_CHECK_ARG(aux_rowmap == nullptr && aux_period == 0, "vj_gemm: row-mapped / periodic aux must be fp32");
+    VJ_CHECK_ARG(p.split_k == 1, "vj_gemm: aux epilogues do not combine with split-K");
+    rc = make_tmap_2d(&tX, aux, 0, N, M, ldaux * 2, 32, 32, 2);
     if (rc) return rc;
   } else {
     tX = tD;
