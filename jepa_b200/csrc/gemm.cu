@@ -98,6 +98,42 @@ VJ_DEVINL float gelu_grad_fast(float x) {
   return fmaf(x, pdf, cdf);
 }
 
+// Exact-erf GELU (and its derivative) for two elements at a time in packed fp32x2 arithmetic - the GELU epilogues are
+// bound by FP issue slots, FFMA2 halves them.  erf via Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5, two orders below
+// the bf16 rounding of the result); exp(-x^2/2) is shared between erf and the Gaussian pdf of the derivative.
+//   g = x Phi(x),  d = Phi(x) + x pdf(x)   (d only if GRAD)
+template <bool GRAD>
+VJ_DEVINL void gelu_pair(float& x0, float& x1, float& d0, float& d1) {
+  const uint64_t x2 = pk2(x0, x1);
+  const uint64_t one2 = pk2(1.0f, 1.0f), half2 = pk2(0.5f, 0.5f), mhalf2 = pk2(-0.5f, -0.5f);
+  // e = exp(-x^2 / 2) = 2^(-x^2 * 0.5 log2(e))
+  const uint64_t y2 = mul2(mul2(x2, x2), pk2(0.72134752044448170f, 0.72134752044448170f));
+  float y0, y1;
+  upk2(y2, y0, y1);
+  const uint64_t e2 = pk2(ex2_approx(-y0), ex2_approx(-y1));
+  // t = 1 / (1 + p |x| / sqrt(2))
+  const uint64_t ax2 = pk2(fabsf(x0), fabsf(x1));
+  const uint64_t den2 = fma2(ax2, pk2(0.33267253f, 0.33267253f), one2);   // 0.47047 / sqrt(2)
+  float n0, n1;
+  upk2(den2, n0, n1);
+  const uint64_t t2 = pk2(__fdividef(1.0f, n0), __fdividef(1.0f, n1));
+  uint64_t poly2 = fma2(t2, pk2(0.7478556f, 0.7478556f), pk2(-0.0958798f, -0.0958798f));
+  poly2 = fma2(poly2, t2, pk2(0.3480242f, 0.3480242f));
+  poly2 = mul2(poly2, t2);
+  const uint64_t pe2 = mul2(poly2, e2);               // 1 - erf(|x| / sqrt 2)
+  const uint64_t h2 = fma2(pe2, mhalf2, half2);       // 0.5 erf(|x| / sqrt 2)
+  float h0, h1;
+  upk2(h2, h0, h1);
+  const uint64_t cdf2 = add2(pk2(copysignf(h0, x0), copysignf(h1, x1)), half2);
+  if (GRAD) {
+    const uint64_t dd2 = fma2(mul2(x2, pk2(0.39894228040143268f, 0.39894228040143268f)), e2, cdf2);
+    upk2(dd2, d0, d1);
+  } else {
+    d0 = x0; d1 = x1;
+  }
+  upk2(mul2(x2, cdf2), x0, x1);
+}
+
 // EPI is a compile-time epilogue kind so that e.g. the plain / GELU kernels carry none of the aux-tile code
 // (and registers) of the residual / dGELU ones.
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, int EPI, bool AUX32, bool RING>
@@ -418,13 +454,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 4; ++j) {
             float d[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = f[8 * j + e];
-              const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
-              if (EPI == VJ_EPI_GELU_GRAD) d[e] = fmaf(x, 0.39894228040143268f * __expf(-0.5f * x * x), cdf);
-              else d[e] = x;
-              f[8 * j + e] = x * cdf;
-            }
+            for (int e = 0; e < 8; e += 2)
+              gelu_pair<EPI == VJ_EPI_GELU_GRAD>(f[8 * j + e], f[8 * j + e + 1], d[e], d[e + 1]);
             if (second) {
               uint4 o;
               o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
