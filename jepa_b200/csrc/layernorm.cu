@@ -88,6 +88,87 @@ ln_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __r
   }
 }
 
+// bf16 -> bf16 forward (the residual stream of both networks): two rows per warp iteration, rows kept packed.
+template <int NV>
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))
+ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int T, int D,
+               float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const float invD = 1.0f / D;
+  auto unpack = [](const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+  };
+  for (long long row0 = 2 * ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)); row0 < T;
+       row0 += 2LL * gridDim.x * wpb) {
+    uint4 xp[2][NV];
+    bool ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      ok[r] = row0 + r < T;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        xp[r][i] = (ok[r] && c < nvec) ? *reinterpret_cast<const uint4*>(x + (row0 + r) * D + c * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float f[8];
+        unpack(xp[r][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+      }
+      mean[r] = warp_sum(s) * invD;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < nvec) {
+          float f[8];
+          unpack(xp[r][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - mean[r];
+            ss = fmaf(d, d, ss);
+          }
+        }
+      }
+      rstd[r] = rsqrtf(warp_sum(ss) * invD + eps);
+      if (lane == 0 && ok[r]) {
+        if (mean_out) mean_out[row0 + r] = mean[r];
+        if (rstd_out) rstd_out[row0 + r] = rstd[r];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float g[8], b[8];   // gamma / beta come from L1 (same few KB for every row)
+        ld8<true>(gamma, c * 8, g);
+        ld8<true>(beta, c * 8, b);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float f[8], o[8];
+          unpack(xp[r][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf((f[j] - mean[r]) * rstd[r], g[j], b[j]);
+          if (ok[r]) st8<false>(y, (row0 + r) * D + c * 8, o);
+        }
+      }
+    }
+  }
+}
+
 // dx = dres + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).  The row (x, dy) stays in registers in
 // its storage format between the two passes; dgamma/dbeta partial sums live in per-warp shared-memory
 // slices (no atomics, no persistent registers), reduced per block into [gridDim.x, D] partials.
@@ -106,8 +187,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, 
   const float invD = 1.0f / D;
   float* my_dg = sm + (size_t)wib * 2 * D;
   float* my_db = my_dg + D;
-  for (int i = lane; i < 2 * D; i += 32) my_dg[i] = 0.f;
-  __syncwarp();
+  // a lane owns the same 8*NV columns for every row it visits: dgamma / dbeta partials live in registers and reach
+  // shared memory once, at the end
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
   for (long long row = (long long)blockIdx.x * wpb + wib; row < T; row += (long long)gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     float xv[NV][X_F32 ? 8 : 1];
@@ -156,20 +242,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, 
         dyf[0] = bf16_lo(dyp[i].x); dyf[1] = bf16_hi(dyp[i].x); dyf[2] = bf16_lo(dyp[i].y); dyf[3] = bf16_hi(dyp[i].y);
         dyf[4] = bf16_lo(dyp[i].z); dyf[5] = bf16_hi(dyp[i].z); dyf[6] = bf16_lo(dyp[i].w); dyf[7] = bf16_hi(dyp[i].w);
         ld8<true>(gamma, c * 8, g);
-        float4* pg = reinterpret_cast<float4*>(my_dg + c * 8);
-        float4* pb = reinterpret_cast<float4*>(my_db + c * 8);
-        float4 g0 = pg[0], g1 = pg[1], b0 = pb[0], b1 = pb[1];
-        float xh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[j] = (xf[j] - mu) * rs;
-          o[j] = rs * (g[j] * dyf[j] - s1 - xh[j] * s2);
+          const float xh = (xf[j] - mu) * rs;
+          o[j] = rs * (g[j] * dyf[j] - s1 - xh * s2);
+          ag[i][j] = fmaf(dyf[j], xh, ag[i][j]);
+          ab[i][j] += dyf[j];
         }
-        g0.x += dyf[0] * xh[0]; g0.y += dyf[1] * xh[1]; g0.z += dyf[2] * xh[2]; g0.w += dyf[3] * xh[3];
-        g1.x += dyf[4] * xh[4]; g1.y += dyf[5] * xh[5]; g1.z += dyf[6] * xh[6]; g1.w += dyf[7] * xh[7];
-        b0.x += dyf[0]; b0.y += dyf[1]; b0.z += dyf[2]; b0.w += dyf[3];
-        b1.x += dyf[4]; b1.y += dyf[5]; b1.z += dyf[6]; b1.w += dyf[7];
-        pg[0] = g0; pg[1] = g1; pb[0] = b0; pb[1] = b1;
         if (dres) {
           float r[8];
           ld8<X_F32>(dres, row * D + c * 8, r);
@@ -178,6 +257,18 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, 
         }
         st8<X_F32>(dx, row * D + c * 8, o);
       }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float4* pg = reinterpret_cast<float4*>(my_dg + c * 8);
+      float4* pb = reinterpret_cast<float4*>(my_db + c * 8);
+      pg[0] = make_float4(ag[i][0], ag[i][1], ag[i][2], ag[i][3]);
+      pg[1] = make_float4(ag[i][4], ag[i][5], ag[i][6], ag[i][7]);
+      pb[0] = make_float4(ab[i][0], ab[i][1], ab[i][2], ab[i][3]);
+      pb[1] = make_float4(ab[i][4], ab[i][5], ab[i][6], ab[i][7]);
     }
   }
   __syncthreads();
@@ -224,6 +315,126 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
   }
 }
 
+// bf16 residual-stream variant (what the training step uses): a warp walks TWO rows per iteration so that twice the
+// bytes are in flight per SM (the kernel is latency-bound otherwise: one row's loads, then two dependent warp
+// reductions, then the stores), dgamma / dbeta partials stay in registers (a lane owns the same 8*NV columns for
+// every row) and reach shared memory once at the end.
+template <int NV>
+__global__ void __launch_bounds__(256, NV <= 2 ? 2 : 1)
+ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+               const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dres,
+               __nv_bfloat16* __restrict__ dx, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int T,
+               int D) {
+  extern __shared__ float sm[];  // [warps][2][D]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const float invD = 1.0f / D;
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  auto unpack = [](const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+  };
+  for (long long row0 = 2 * ((long long)blockIdx.x * wpb + wib); row0 < T; row0 += 2LL * gridDim.x * wpb) {
+    uint4 xp[2][NV], dyp[2][NV], rp[2][NV];
+    float mu[2], rs[2];
+    bool ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long row = row0 + r;
+      ok[r] = row < T;
+      mu[r] = ok[r] ? mean[row] : 0.f;
+      rs[r] = ok[r] ? rstd[row] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = ok[r] && c < nvec;
+        xp[r][i] = in ? *reinterpret_cast<const uint4*>(x + row * D + c * 8) : make_uint4(0, 0, 0, 0);
+        dyp[r][i] = in ? *reinterpret_cast<const uint4*>(dy + row * D + c * 8) : make_uint4(0, 0, 0, 0);
+        rp[r][i] = (in && dres) ? *reinterpret_cast<const uint4*>(dres + row * D + c * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float g[8];
+        ld8<true>(gamma, c * 8, g);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float xf[8], dyf[8];
+          unpack(xp[r][i], xf);
+          unpack(dyp[r][i], dyf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gy = g[j] * dyf[j];
+            s1[r] += gy;
+            s2[r] = fmaf(gy, (xf[j] - mu[r]) * rs[r], s2[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      s1[r] = warp_sum(s1[r]) * invD;
+      s2[r] = warp_sum(s2[r]) * invD;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float g[8];
+        ld8<true>(gamma, c * 8, g);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float xf[8], dyf[8], rf[8], o[8];
+          unpack(xp[r][i], xf);
+          unpack(dyp[r][i], dyf);
+          unpack(rp[r][i], rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xf[j] - mu[r]) * rs[r];
+            o[j] = fmaf(rs[r], g[j] * dyf[j] - s1[r] - xh * s2[r], rf[j]);
+            ag[i][j] = fmaf(dyf[j], xh, ag[i][j]);   // rows past T carry dy = 0
+            ab[i][j] += dyf[j];
+          }
+          if (ok[r]) st8<false>(dx, (row0 + r) * D + c * 8, o);
+        }
+      }
+    }
+  }
+  float* my_dg = sm + (size_t)wib * 2 * D;
+  float* my_db = my_dg + D;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float4* pg = reinterpret_cast<float4*>(my_dg + c * 8);
+      float4* pb = reinterpret_cast<float4*>(my_db + c * 8);
+      pg[0] = make_float4(ag[i][0], ag[i][1], ag[i][2], ag[i][3]);
+      pg[1] = make_float4(ag[i][4], ag[i][5], ag[i][6], ag[i][7]);
+      pb[0] = make_float4(ab[i][0], ab[i][1], ab[i][2], ab[i][3]);
+      pb[1] = make_float4(ab[i][4], ab[i][5], ab[i][6], ab[i][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < wpb; ++w) {
+      a += sm[(size_t)w * 2 * D + i];
+      b += sm[(size_t)w * 2 * D + D + i];
+    }
+    part_dgamma[(long long)blockIdx.x * D + i] = a;
+    part_dbeta[(long long)blockIdx.x * D + i] = b;
+  }
+}
+
 static int ln_grid(int T) {
   long long g = (T + 7) / 8;
   const long long cap = (long long)num_sms() * 8;
@@ -231,6 +442,8 @@ static int ln_grid(int T) {
   if (g < 1) g = 1;
   return int(g);
 }
+// upper bound on the number of blocks any ln_bwd launch uses (sizes the partials workspace); the launchers pick
+// a whole number of resident waves below it
 static int ln_bwd_grid(int T) {
   long long g = (T + 7) / 8;
   const long long cap = (long long)num_sms() * 4;
@@ -246,11 +459,17 @@ static void launch_ln_fwd(const void* x, int x_f32, void* y, int y_f32, const fl
   if (x_f32 && y_f32) ln_fwd_kernel<NV, true, true><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
   else if (x_f32) ln_fwd_kernel<NV, true, false><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
   else if (y_f32) ln_fwd_kernel<NV, false, true><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
-  else ln_fwd_kernel<NV, false, false><<<grid, 256, 0, s>>>(x, y, gamma, beta, mean, rstd, T, D, eps);
+  else {
+    // one resident wave of two-row warps
+    long long g2 = (long long)num_sms() * (NV <= 2 ? 3 : (NV <= 4 ? 2 : 1));
+    if (g2 > (T + 15) / 16) g2 = (T + 15) / 16;
+    ln_fwd2_kernel<NV><<<int(g2), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                               gamma, beta, mean, rstd, T, D, eps);
+  }
 }
 
 template <int NV>
-static void launch_ln_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean,
+static int launch_ln_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean,
                           const float* rstd, const void* dres, void* dx, float* pg, float* pb, int grid, int T, int D,
                           cudaStream_t s) {
   const size_t smem = (size_t)8 * 2 * D * sizeof(float);
@@ -260,12 +479,29 @@ static void launch_ln_bwd(const void* dy, const void* x, int x_f32, const float*
     cudaFuncSetAttribute(ln_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4);
     configured = true;
   }
-  if (x_f32)
-    ln_bwd_kernel<NV, true><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
-                                                    dres, dx, pg, pb, T, D);
-  else
+  if (NV > 5 && !x_f32) {   // D > 1280: the two-row kernel would spill; one row per iteration
     ln_bwd_kernel<NV, false><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
                                                      dres, dx, pg, pb, T, D);
+  } else if (x_f32) {
+    ln_bwd_kernel<NV, true><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
+                                                    dres, dx, pg, pb, T, D);
+  } else {
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaFuncSetAttribute(ln_bwd2_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4);
+      configured2 = true;
+    }
+    // exactly one resident wave (the grid-stride loop balances rows; a partial second wave would double the time)
+    long long g2 = (long long)num_sms() * (NV <= 2 ? 2 : 1);
+    if (g2 > (T + 15) / 16) g2 = (T + 15) / 16;
+    if (g2 > grid) g2 = grid;
+    grid = int(g2);
+    ln_bwd2_kernel<NV><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                               reinterpret_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+                                               reinterpret_cast<const __nv_bfloat16*>(dres),
+                                               reinterpret_cast<__nv_bfloat16*>(dx), pg, pb, T, D);
+  }
+  return grid;
 }
 
 }  // namespace vj
@@ -308,11 +544,11 @@ extern "C" int vj_layernorm_bwd(const void* dy, const void* x, int x_f32, const 
   if (T <= 0) return 0;
   VJ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "vj_layernorm_bwd: null pointer");
   VJ_CHECK_ARG(D % 8 == 0 && D <= 2048, "vj_layernorm_bwd: D=%d unsupported (multiple of 8, <= 2048)", D);
-  const int grid = ln_bwd_grid(T);
+  int grid = ln_bwd_grid(T);
   VJ_CHECK_ARG(ws_bytes >= (size_t)grid * 2 * D * sizeof(float), "vj_layernorm_bwd: workspace too small");
   float* pg = reinterpret_cast<float*>(workspace);
   float* pb = pg + (size_t)grid * D;
-#define VJ_CALL(NV) launch_ln_bwd<NV>(dy, x, x_f32, gamma, mean, rstd, dres, dx, pg, pb, grid, T, D, s)
+#define VJ_CALL(NV) grid = launch_ln_bwd<NV>(dy, x, x_f32, gamma, mean, rstd, dres, dx, pg, pb, grid, T, D, s)
   VJ_LN_DISPATCH(D, VJ_CALL);
 #undef VJ_CALL
   VJ_CUDA(cudaGetLastError());
