@@ -24,7 +24,6 @@ struct AttnBwdParams {
   __nv_bfloat16* dqkv;
   int H, T;
   float scale, scale_log2;
-  int dbg;   // VJ_DBG_ATTN ablation bits (timing experiments only; results are wrong when non-zero)
 };
 
 template <int HD>
@@ -45,9 +44,6 @@ struct BwdCfg {
   static constexpr int DKV_TMEM = (128 + (CAN_FUSE_DQ ? 3 : 2) * HD) <= 256 ? 256 : 512;
   static constexpr int DQ_TMEM = (128 + HD) <= 256 ? 256 : 512;
 };
-
-__device__ long long g_attn_ts[16 * 64];   // TEMP: timeline instrumentation
-#define TS(slot) do { if (ts_on && lane == 0) g_attn_ts[i * 16 + (slot)] = clock64(); } while (0)
 
 VJ_DEVINL void named_bar_sync_attn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -141,7 +137,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   const uint32_t bar_stat = smem_u32(bars + 11), bar_statfree = smem_u32(bars + 13);   // [2] each
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool ts_on = (p.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 8 && (warp == 1 || warp == 2);
   if (threadIdx.x == 0) {
     mbar_init(bar_kv, 1); mbar_init(bar_s, 1);
     for (int st = 0; st < 2; ++st) {
@@ -236,7 +231,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const uint32_t sQi = sQ + st * B::STAGE_BYTES, sDOi = sDO + st * B::STAGE_BYTES;
         if (ST == 1 || i == 0) issue_S(i);    // S^T = K Q_i^T
         mbar_wait(bar_p, ph);
-        TS(9);
         tc_fence_after();
         // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
 #pragma unroll
@@ -245,19 +239,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         umma_commit(bar_dp);
         // dV += P^T dO_i
 #pragma unroll
-        for (int kk = 0; kk < ((p.dbg & 8) ? 1 : 8); ++kk)
+        for (int kk = 0; kk < 8; ++kk)
           umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
         umma_commit(bar_pvdone);
-        TS(10);
         mbar_wait(bar_ds, ph);
-        TS(11);
         tc_fence_after();
         if (ST == 2 && i + 1 < n_q) issue_S(i + 1);
         // dK += dS^T Q_i
 #pragma unroll
-        for (int kk = 0; kk < ((p.dbg & 8) ? 1 : 8); ++kk)
+        for (int kk = 0; kk < 8; ++kk)
           umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
-        if (FUSE_DQ && !(p.dbg & 2)) {
+        if (FUSE_DQ) {
           // dQ_i partial [q, hd] = dS_i [q, kv] K [kv, hd]: A = dS^T tile as M-major (q contiguous), B = K MN-major
           constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);
 #pragma unroll
@@ -266,7 +258,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         umma_commit(bar_qdofree + 8 * st);
         umma_commit(bar_psfree);
-        TS(12);
       }
     }
     __syncwarp();
@@ -296,7 +287,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && !(p.dbg & 1)) {
+      if (lane == 0) {
         tma_reduce_add_2d(&tmDQ, dqs, head * HD, row_begin + qi * 128 + qd * 32);
         tma_commit_group();
       }
@@ -306,9 +297,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       const uint32_t lse_s = stats + (i & 1) * 1024 + 4 * col0;
       const uint32_t del_s = lse_s + 512;
       mbar_wait(bar_stat + 8 * (i & 1), uint32_t(i >> 1) & 1);
-      TS(0);
       mbar_wait(bar_s, ph);
-      TS(1);
       tc_fence_after();
       uint32_t pk[32];
 #pragma unroll
@@ -319,11 +308,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 L = lds128f(lse_s + 4 * (c * 32 + e));
-          float a0 = fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x);
-          float a1 = fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y);
-          float a2 = fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z);
-          float a3 = fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w);
-          if (!(p.dbg & 4)) { a0 = ex2_approx(a0); a1 = ex2_approx(a1); a2 = ex2_approx(a2); a3 = ex2_approx(a3); }
+          const float a0 = ex2_approx(fmaf(__uint_as_float(v[e]), p.scale_log2, -L.x));
+          const float a1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -L.y));
+          const float a2 = ex2_approx(fmaf(__uint_as_float(v[e + 2]), p.scale_log2, -L.z));
+          const float a3 = ex2_approx(fmaf(__uint_as_float(v[e + 3]), p.scale_log2, -L.w));
           pk[c * 16 + e / 2] = pack_bf16x2(a0, a1);
           pk[c * 16 + e / 2 + 1] = pack_bf16x2(a2, a3);
         }
@@ -335,12 +323,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         // the P/dS tile is free once the previous iteration's dK (and dQ) MMAs retired; by then the dQ partial of
         // tile i-1 is complete as well (drained below)
-        if (c == 0) TS(2);
         if (c == 0 && i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
-        if (c == 0) TS(3);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (!(p.dbg & 16))
           ptile_store(ps, r, half * 8 + c * 4 + g,
                       make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]));
       }
@@ -348,13 +333,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      TS(4);
       // bar_psfree(i-1) was observed above, so the dQ partial of tile i-1 is complete: drain it now, off the MMA
       // warp's critical path (it is busy with dP^T / dV).
-      if (FUSE_DQ && half == 0 && i > 0 && !(p.dbg & 2)) { tc_fence_after(); drain_dq(i - 1); }
-      TS(5);
+      if (FUSE_DQ && half == 0 && i > 0) { tc_fence_after(); drain_dq(i - 1); }
       mbar_wait(bar_dp, ph);
-      TS(6);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -371,23 +353,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           ds[e / 2 + 1] = mul_bf16x2(pk[c * 16 + e / 2 + 1],
                                      pack_bf16x2(__uint_as_float(v[e + 2]) - Dl.z, __uint_as_float(v[e + 3]) - Dl.w));
         }
-        if (c == 0) mbar_wait(bar_pvdone, ph);
-        if (c == 0) TS(7);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
+        if (c == 0) mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (!(p.dbg & 16))
           ptile_store(ps, r, half * 8 + c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_ds); mbar_arrive(bar_statfree + 8 * (i & 1)); }
-      TS(8);
     }
     // epilogue: half-0 warps store dV, half-1 warps dK (x scale) -> bf16 -> dqkv[:, v / k third], 32 columns at a time
     mbar_wait(bar_psfree, (n_q - 1) & 1);
     tc_fence_after();
-    if (FUSE_DQ && half == 0 && !(p.dbg & 2)) drain_dq(n_q - 1);
+    if (FUSE_DQ && half == 0) drain_dq(n_q - 1);
     const int rows_valid = max(0, min(32, len - kv0 - qd * 32));
     const uint32_t stage = ps + (warp - 2) * 2048;
     const uint32_t tmem_src = half == 0 ? tmem_dV : tmem_dK;
@@ -650,8 +629,6 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   AttnBwdParams p;
   p.cu_seqlens = cu; p.lse2 = lse2; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.H = H; p.T = T; p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  static const int dbg = getenv("VJ_DBG_ATTN") ? atoi(getenv("VJ_DBG_ATTN")) : 0;
-  p.dbg = dbg;
   dim3 grid((max_len + 127) / 128, nseq, H);
   if (fuse) {
     kdkv_fused<<<grid, kDkvThreads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
@@ -674,10 +651,6 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
 }
 
 }  // namespace vj
-
-extern "C" int vj_debug_attn_ts(long long* out, int n) {   // TEMP
-  return (int)cudaMemcpyFromSymbol(out, vj::g_attn_ts, sizeof(long long) * n);
-}
 
 extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta_ws,
                            void* dqkv, float* dq_acc_ws, const int* cu_seqlens, int nseq, int max_len, int H, int HD,

@@ -43,10 +43,7 @@ struct GemmParams {
   int has_auxout;
   int reduce_add;
   float alpha;
-  // smem-descriptor strides (bytes); overridable through VJ_DBG_* env vars while bringing the
-  // kernel up on hardware.
-  unsigned lbo_k, sbo_k, lbo_mn, sbo_mn;
-  int dbg;   // TEMP ablation bits (VJ_DBG_GEMM)
+  unsigned lbo_k, sbo_k, lbo_mn, sbo_mn;   // smem-descriptor strides (bytes) of the K-major / MN-major operand tiles
 };
 
 constexpr int kAuxRing = 3;          // aux tiles (32 x 32 bf16 = 2 KB) in flight per epilogue warp
@@ -345,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (p.aux_rowmap != nullptr) srow = p.aux_rowmap[grow];
               else if (p.aux_period > 0) srow = grow % p.aux_period;
               const long long ecol = n0 + col0 + ach * (a128 ? 4 : 8);
-              if (ecol < p.N && !(p.dbg & 2)) {
+              if (ecol < p.N) {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.aux) + (srow * p.ldaux + ecol) * (a128 ? 4 : 2);
                 val = __ldg(reinterpret_cast<const uint4*>(src));
               }
@@ -484,7 +481,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0 && !(p.dbg & 1)) {
+        if (lane == 0) {
           if (two_stores) tma_store_2d(&tmX, bufB, n0 + col0, row0);
           if (OUT_F32 && p.reduce_add) tma_reduce_add_2d(&tmD, bufA, n0 + col0, row0);
           else tma_store_2d(&tmD, bufA, n0 + col0, row0);
@@ -599,11 +596,6 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.reduce_add = (accumulate || p.split_k > 1) ? 1 : 0;
   p.alpha = alpha;
   p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;
-  p.dbg = getenv("VJ_DBG_GEMM") ? atoi(getenv("VJ_DBG_GEMM")) : 0;
-  if (const char* e = getenv("VJ_DBG_LBO_K")) p.lbo_k = unsigned(atoi(e));
-  if (const char* e = getenv("VJ_DBG_SBO_K")) p.sbo_k = unsigned(atoi(e));
-  if (const char* e = getenv("VJ_DBG_LBO_MN")) p.lbo_mn = unsigned(atoi(e));
-  if (const char* e = getenv("VJ_DBG_SBO_MN")) p.sbo_mn = unsigned(atoi(e));
 
   CUtensorMap tA, tB, tD, tX;
   int rc;

@@ -175,7 +175,7 @@ ln_fwd2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
 template <int NV, bool X_F32>
 // (register caps chosen so nothing spills: with ~220 KB of the SM given to shared memory L1 is tiny and every
 // local-memory access is an L2 round trip)
-__global__ void __launch_bounds__(256, NV <= 2 ? 3 : (NV <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(256, NV <= 2 ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const void* __restrict__ dres,
               void* __restrict__ dx, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta, int T, int D) {
@@ -479,12 +479,12 @@ static int launch_ln_bwd(const void* dy, const void* x, int x_f32, const float* 
     cudaFuncSetAttribute(ln_bwd_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4);
     configured = true;
   }
-  if (NV > 5 && !x_f32) {   // D > 1280: the two-row kernel would spill; one row per iteration
-    ln_bwd_kernel<NV, false><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
-                                                     dres, dx, pg, pb, T, D);
-  } else if (x_f32) {
+  if (x_f32) {
     ln_bwd_kernel<NV, true><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
                                                     dres, dx, pg, pb, T, D);
+  } else if constexpr (NV > 5) {   // D > 1280: the two-row kernel would spill; one row per iteration
+    ln_bwd_kernel<NV, false><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd,
+                                                     dres, dx, pg, pb, T, D);
   } else {
     static bool configured2 = false;
     if (!configured2) {

@@ -152,7 +152,6 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
   return bad ? 1 : 0;
 }
 
-extern "C" int vj_debug_attn_ts(long long* out, int n);
 static void perf(int H, int HD, int nseq, int L, bool bwd) {
   const int T = nseq * L, W = 3 * H * HD, D = H * HD;
   std::vector<int> cu(nseq + 1);
@@ -189,17 +188,6 @@ static void perf(int H, int HD, int nseq, int L, bool bwd) {
 int main(int argc, char** argv) {
   const bool bwd = !(argc > 1 && !strcmp(argv[1], "fwd"));
   int fails = 0;
-  if (argc > 1 && !strcmp(argv[1], "ts")) {   // TEMP: per-tile timeline of one CTA
-    perf(16, 32, 32, 1184, true);
-    long long ts[160];
-    vj_debug_attn_ts(ts, 160);
-    for (int i = 0; i < 10; ++i) {
-      printf("tile %d:", i);
-      for (int k = 0; k < 13; ++k) printf(" %lld", ts[i * 16 + k] - ts[0]);
-      printf("\n");
-    }
-    return 0;
-  }
   if (argc > 1 && !strcmp(argv[1], "perf")) {   // timing only (ablation experiments)
     perf(16, 64, 32, 1568, false);
     perf(16, 32, 32, 1184, false);
