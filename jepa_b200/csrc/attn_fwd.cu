@@ -41,25 +41,32 @@ struct FwdCfg {
   static constexpr int P_OFF = 4 * A::TILE_BYTES;
   static constexpr int BAR_OFF = P_OFF + A::P_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;
-  static constexpr int TMEM_COLS = (128 + HD) <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = (128 + HD + 64) <= 256 ? 256 : 512;   // S (fp32) | O (fp32) | P (bf16 pairs)
 };
 
-// p = 2^(s*scale - moff) for 32 score columns, summed into l and packed to bf16 pairs; FULL = no tail masking
-template <bool FULL>
+// p = 2^(s*scale - moff) for 32 score columns, summed into l, packed to bf16 and handed to `emit(g, uint4)` eight
+// columns at a time (only four packed registers are live); FULL = no tail masking
+template <bool FULL, typename Emit>
 VJ_DEVINL void exp_pack32(const uint32_t (&sv)[32], int base, int valid, float scale_log2, float moff, float& l,
-                          uint32_t (&out)[16]) {
+                          Emit&& emit) {
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float a = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -moff));
-    float b = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -moff));
-    if (!FULL) {
-      a = (base + i < valid) ? a : 0.f;
-      b = (base + i + 1 < valid) ? b : 0.f;
+  for (int g = 0; g < 4; ++g) {
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 8 * g + 2 * k;
+      float a = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -moff));
+      float b = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -moff));
+      if (!FULL) {
+        a = (base + i < valid) ? a : 0.f;
+        b = (base + i + 1 < valid) ? b : 0.f;
+      }
+      l0 += a;
+      l1 += b;
+      o[k] = pack_bf16x2(a, b);
     }
-    l0 += a;
-    l1 += b;
-    out[i >> 1] = pack_bf16x2(a, b);
+    emit(g, make_uint4(o[0], o[1], o[2], o[3]));
   }
   l += l0 + l1;
 }
@@ -107,6 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_P = tmem_base + 128 + HD;   // P_j as bf16 pairs: the A operand of the PV MMA, never in smem
 
   const uint32_t sQ = smem_u32(smem + F::Q_OFF), sK = smem_u32(smem + F::K_OFF);
   const uint32_t sV = smem_u32(smem + F::V_OFF), sP = smem_u32(smem + F::P_OFF);
@@ -162,7 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_O, ptile_desc(sP, kk), mnmajor_desc<HD>(sV, kk), idesc_o, (j > 0 || kk > 0));
+          umma_f16_ts(tmem_O, tmem_P + kk * 8, mnmajor_desc<HD>(sV, kk), idesc_o, (j > 0 || kk > 0));
         umma_commit(bar_vfree);
       }
     }
@@ -173,7 +181,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     float m_ref = -INFINITY;                 // reference max the accumulators are expressed against
     float l = 0.f;
-    const uint32_t prow = sP + r * 128;
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(128, len - j * 128);
       mbar_wait(bar_s, j & 1);
@@ -231,13 +238,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
       // the single P tile is free once PV_{j-1} retired (long done by now); each 32-column group is exponentiated,
       // packed and stored right away so only 16 packed registers are live at a time (no spills in this loop).
       if (j > 0) mbar_wait(bar_vfree, (j - 1) & 1);
-      auto put = [&](const uint32_t (&pk)[16], int g0) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col8 = g0 + g;
-          sts128(prow + (col8 >> 3) * 16384 + (((col8 & 7) ^ (r & 7)) << 4),
-                 make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]));
-        }
+      auto put = [&](int col8, const uint4& u) {   // 8 probabilities (4 bf16 pairs) of this row -> P columns in TMEM
+        tmem_st4(tmem_P + lane_addr + col8 * 4, u);
       };
       auto reload_last = [&]() {   // columns 96..127 again (into s0, dead by now), then S_j is handed back to the MMA warp
         tmem_ld32(tmem_S + lane_addr + 96, s0);
@@ -246,22 +248,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
       };
-      {
-        uint32_t pk[16];
-        if (valid == 128) {
-          exp_pack32<true>(s0, 0, valid, p.scale_log2, moff, l, pk); put(pk, 0);
-          exp_pack32<true>(s1, 32, valid, p.scale_log2, moff, l, pk); put(pk, 4);
-          exp_pack32<true>(s2, 64, valid, p.scale_log2, moff, l, pk); put(pk, 8);
-          reload_last(); exp_pack32<true>(s0, 96, valid, p.scale_log2, moff, l, pk); put(pk, 12);
-        } else {
-          exp_pack32<false>(s0, 0, valid, p.scale_log2, moff, l, pk); put(pk, 0);
-          exp_pack32<false>(s1, 32, valid, p.scale_log2, moff, l, pk); put(pk, 4);
-          exp_pack32<false>(s2, 64, valid, p.scale_log2, moff, l, pk); put(pk, 8);
-          reload_last(); exp_pack32<false>(s0, 96, valid, p.scale_log2, moff, l, pk); put(pk, 12);
-        }
+      if (valid == 128) {
+        exp_pack32<true>(s0, 0, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(g, u); });
+        exp_pack32<true>(s1, 32, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(4 + g, u); });
+        exp_pack32<true>(s2, 64, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(8 + g, u); });
+        reload_last();
+        exp_pack32<true>(s0, 96, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(12 + g, u); });
+      } else {
+        exp_pack32<false>(s0, 0, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(g, u); });
+        exp_pack32<false>(s1, 32, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(4 + g, u); });
+        exp_pack32<false>(s2, 64, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(8 + g, u); });
+        reload_last();
+        exp_pack32<false>(s0, 96, valid, p.scale_log2, moff, l, [&](int g, const uint4& u) { put(12 + g, u); });
       }
+      tmem_wait_st();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
     }
