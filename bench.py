@@ -187,6 +187,19 @@ def train_step(st, clips, masks_enc, masks_pred):
     return loss.detach()
 
 
+def ncu_gemm_traffic(cfg_name):
+    """DRAM bytes moved by the GEMM family in one step, from the committed ncu launch list of `bench.py --profile`
+    (profiles/, vitl16 only); None when no capture exists for this config."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_launches_final_summary.txt")
+    if cfg_name != "vitl16" or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        for line in f:
+            if line.startswith("# gemm family:"):
+                return int(float(line.split("DRAM traffic")[1].split("GB")[0]) * 1e9)
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from jepa_b200 import _lib
@@ -339,7 +352,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "vj::gemm_kernel (all Linear / patch-embed GEMMs of a step)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                         "traffic": ncu_gemm_traffic(args.config), "traffic_unit": "DRAM bytes per step over the family's launches "
+                         "(dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_step_launches_final.csv)",
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained",
                          "launches_per_step": n_gemm // roof_steps, "gemm_ms_per_step": round(gemm_ms_step, 3),
                          "executed_tflop_per_step": round(gemm_flops_exec / roof_steps / 1e12, 3),
                          "step_tflops": round(f_clip * B / (ms_step * 1e-3) / 1e12, 1),
