@@ -184,9 +184,11 @@ def test_patch_embed_matches_oracle(dev):
     assert torch.equal(outk.view(B, Kk, D), Kn.gather_rows(out.view(B, 784, D), m))
 
 
-@pytest.mark.parametrize("H,hd,lens", [(3, 64, [208, 160]), (16, 24, [296, 40, 128]), (3, 128, [200, 72])])
+@pytest.mark.parametrize("H,hd,lens", [(3, 64, [208, 160]), (16, 24, [296, 40, 128]), (3, 128, [200, 72]),
+                                       (4, 80, [300, 100])])
 def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
-    """Attention (modules.py:61-78 core) incl. the zero-padded hd=24 heads, ragged sequence tails."""
+    """Attention (modules.py:61-78 core) incl. the zero-padded heads (predictor hd=24 -> 32, ViT-H hd=80 -> 128),
+    ragged sequence tails."""
     from jepa_b200 import kernels as Kn
     from jepa_b200.params import padded_head_dim
     hdp = padded_head_dim(hd)
