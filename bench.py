@@ -393,7 +393,10 @@ def oracle_step_fn(cfg_name, B):
         for k, v in S.items():
             if k != frozen:
                 v.requires_grad_(True)
-    me, mp = seeded_masks(crop, frames, B, seed=0)
+    # the GPU arm's masks (collator call at ITS batch size, seed 0), first B rows: identical kept-token counts per clip,
+    # i.e. the same work per clip on both arms (a batch-1 collator call would keep more context tokens)
+    me, mp = seeded_masks(crop, frames, CONFIGS[cfg_name][6], seed=0)
+    me, mp = [m[:B].clone() for m in me], [m[:B].clone() for m in mp]
     clips = torch.randn(B, 3, frames, crop, crop, generator=torch.Generator().manual_seed(0))
 
     def step():
@@ -466,7 +469,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = B * args.steps / dt
     N = (frames // 2) * (crop // 16) ** 2
-    me, mp = seeded_masks(crop, frames, B, seed=0)
+    me, mp = seeded_masks(crop, frames, Bcfg, seed=0)   # same masks as the GPU arm (see oracle_step_fn)
     Ke, Kp = [int(m.shape[1]) for m in me], [int(m.shape[1]) for m in mp]
     sample = (f"each step = one fp32 train step of the CPU oracle port on {B} clip of {args.config} "
               f"({model_name}, {frames}x{crop}x{crop}, masks Ke={Ke} Kp={Kp}); {cores} host threads")
