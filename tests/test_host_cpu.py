@@ -212,3 +212,19 @@ def test_product_path_never_imports_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     text = open(os.path.join(dp, f)).read()
                     assert "oracle" not in text.replace("# oracle", ""), f"{dp}/{f} references the oracle"
+
+
+def test_bench_flop_accounting_matches_survey():
+    """bench.py's roofline numerators are the SURVEY.md section 8d / BASELINE.md section 2 figures for the seeded masks."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vj_bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N224 = 8 * 14 * 14
+    assert bench.flops_per_clip(1024, 24, N224, [360, 48], [824, 1144]) == 2_438_801_522_688      # C2/C3 ViT-L/16
+    assert bench.flops_per_clip(1280, 32, N224, [360, 48], [824, 1144]) == 4_455_977_058_304      # C4 ViT-H/16
+    me, mp = bench.seeded_masks(224, 16, 32, seed=0)   # the masks those figures are quoted on
+    assert [m.shape[1] for m in me] == [360, 48] and [m.shape[1] for m in mp] == [824, 1144]
+    g = bench.gemm_flops_per_clip(1024, 24, N224, [360, 48], [824, 1144])
+    f = bench.flops_per_clip(1024, 24, N224, [360, 48], [824, 1144])
+    assert abs((f - g) / f - 0.179) < 2e-3    # attention share 17.9 %
