@@ -145,3 +145,39 @@ def test_init_distributed_without_slurm_returns_single_process(monkeypatch):
     from src.utils.distributed import init_distributed
     monkeypatch.delenv("SLURM_NTASKS", raising=False)
     assert init_distributed() == (1, 0)
+
+
+def test_flat_layout_matches_backward_order():
+    """FlatGradSync relies on the flat gradient buffer becoming final from its END towards its START while the
+    hand-scheduled backward runs (engine.blocks_backward reports `offset(blocks.i.norm1.weight)` after block i):
+    parameters must be registered as [input-side group][block 0]...[block L-1][output-side group], norm1.weight first
+    inside a block.  Guards the registration order of the reference-compatible modules."""
+    from functools import partial
+
+    import torch.nn as nn
+
+    from jepa_b200.models import VisionTransformer, vit_predictor
+    enc = VisionTransformer(img_size=64, patch_size=16, num_frames=4, tubelet_size=2, embed_dim=64, depth=3, num_heads=2,
+                            mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), uniform_power=True)
+    pred = vit_predictor(img_size=64, use_mask_tokens=True, patch_size=16, num_frames=4, tubelet_size=2, embed_dim=64,
+                         predictor_embed_dim=64, depth=2, num_heads=2, uniform_power=True, num_mask_tokens=2,
+                         zero_init_mask_tokens=True)
+    for mod, prefix, head, tail in (
+            (enc, "blocks.", ("patch_embed.", "pos_embed"), ("norm.",)),
+            (pred, "predictor_blocks.", ("predictor_embed.", "mask_tokens.", "predictor_pos_embed"),
+             ("predictor_norm.", "predictor_proj."))):
+        names = [n for n, _ in mod.named_parameters()]
+        kinds = []
+        for n in names:
+            if n.startswith(prefix):
+                kinds.append(1 + int(n[len(prefix):].split(".")[0]))
+            elif n.startswith(head):
+                kinds.append(0)
+            else:
+                assert n.startswith(tail), n
+                kinds.append(10 ** 6)
+        assert kinds == sorted(kinds), names            # head group, blocks ascending, tail group
+        depth = max(k for k in kinds if k < 10 ** 6)
+        for i in range(depth):
+            first = names[kinds.index(1 + i)]
+            assert first == f"{prefix}{i}.norm1.weight", first
