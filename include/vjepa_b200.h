@@ -42,8 +42,10 @@ long long vj_launch_count(void);
  * b_mn = 0: B stored [N,K];                            b_mn = 1: B stored [K,N].
  * Supported (a_mn,b_mn): (0,0) forward / nn.Linear, (0,1) dgrad, (1,1) wgrad.
  * d_f32: D is fp32 (else bf16).  accumulate!=0 or split_k>1 reduce-add into fp32 D.
- * bias: fp32 [N] or NULL.  aux: bf16 or fp32 (aux_f32) tile source for ADD / DGELU; row r reads
- * aux row aux_rowmap[r] if given, else r % aux_period if aux_period > 0, else r.
+ * bias: fp32 [N] or NULL.  aux: bf16 or fp32 (aux_f32) tile source for ADD / MUL / DGELU.  An fp32 aux may be
+ * row-mapped: row r reads aux row aux_rowmap[r] if given, else r % aux_period if aux_period > 0, else r (pos-embed
+ * add of the patch-embed GEMM); a bf16 aux is a plain [M,N] matrix (residual stream / saved gelu') and does not
+ * combine with split-K.  aux_out (bf16 [M,N], optional) is the second output of the GELU epilogues.
  * Replaces F.linear / Conv3d-as-GEMM and their backward:
  *   src/models/utils/modules.py:31-34,63,76; src/models/predictor.py:194,237;
  *   src/models/utils/patch_embed.py:54-57. */
