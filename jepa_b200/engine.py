@@ -9,7 +9,6 @@ epilogue, and the backward is scheduled by hand - dgrad and wgrad GEMMs read the
 in place (MN-major descriptors, no transposes) and the wgrads reduce straight into a flat fp32
 gradient buffer.
 """
-import math
 
 import torch
 

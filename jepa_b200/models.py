@@ -10,12 +10,10 @@ device raises.
 import math
 from functools import partial
 
-import numpy as np
 import torch
 import torch.nn as nn
 
 from . import engine
-from . import kernels as K
 from .params import FlatParamStore
 from .pos_embs import get_2d_sincos_pos_embed, get_3d_sincos_pos_embed
 from .tensors import trunc_normal_

@@ -8,14 +8,13 @@ Stated tolerances (bf16 operands / fp32 accumulation vs the fp32 oracle):
   whole-network activations rel-L2 <= 3e-2, per-parameter gradients rel-L2 <= 6e-2, loss abs 5e-3
   index / gather paths: bit-exact (torch.equal)
 """
-import math
 import os
 import subprocess
 
 import pytest
 import torch
 
-from common import C1, synth_clips
+from common import synth_clips
 from parity_util import (TOL_ACT, c1_masks, compare_step, rel_l2, run_c1_step_cuda, run_c1_step_oracle)
 
 pytestmark = pytest.mark.gpu
