@@ -9,8 +9,8 @@ logging helpers (grad_logger x2, adamw_logger): LR/WD schedule, target forward +
 encoder + predictor forward/backward, L1 loss, GradScaler, AdamW, zero_grad, EMA; N>1 adds the DDP gradient
 all-reduce.  `value` times K such steps with inputs resident in HBM (CUDA events, max over ranks); `e2e`
 repeats them through the public module API with HOST inputs: pinned clips + masks copied to the device and
-the loss read back every step.  `--impl reference` times the CPU oracle port of the same step on the host
-cores (the reference itself is Python and cannot travel to the GPU box).
+the loss read back every step.  `--impl reference` times the UNMODIFIED reference's CPU path (baseline/_ref, its own
+app.vjepa.train.main, fp32) on the host cores; if baseline/_ref is absent it falls back to the CPU oracle port.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -167,8 +167,9 @@ def build_training_state(cfg_name, device, world, rank):
                 scheduler=scheduler, wd_scheduler=wd_scheduler, momentum=momentum)
 
 
-def train_step(st, clips, masks_enc, masks_pred):
-    """train_step() of app/vjepa/train.py:414-498 (logging helpers excluded); returns the loss (device scalar)."""
+def train_step(st, clips, masks_enc, masks_pred, loggers=False):
+    """train_step() of app/vjepa/train.py:414-498; returns the loss (device scalar).  loggers=False is SURVEY 8d's (A)
+    math step (grad_logger x2 / adamw_logger off on both arms), loggers=True the as-shipped step (B)."""
     from jepa_b200 import step as vj
     st["scheduler"].step()
     st["wd_scheduler"].step()
@@ -182,9 +183,58 @@ def train_step(st, clips, masks_enc, masks_pred):
     scaler.unscale_(opt)
     scaler.step(opt)
     scaler.update()
+    if loggers:
+        from src.utils.logging import adamw_logger, grad_logger
+        grad_logger(st["encoder"].named_parameters())
+        grad_logger(st["predictor"].named_parameters())
     opt.zero_grad()
+    if loggers:
+        adamw_logger(opt)
     vj.ema_update(st["encoder"], st["target"], next(st["momentum"]))
     return loss.detach()
+
+
+def ddp_gradient_check(st, clips, masks_enc, masks_pred):
+    """N > 1: the in-backward flat-buffer exchange (jepa_b200.distributed.FlatGradSync) must leave, on every rank, the mean
+    of the per-rank gradients.  One backward WITH the exchange, one without it followed by a plain NCCL all-reduce(AVG) of
+    the whole gradient vector; returns the rel-L2 distance (split-K wgrads are TMA reduce-adds, so the two backward passes
+    differ by fp32 summation order, ~1e-6).  Makes the SCALE run itself prove gradient equality."""
+    import torch.distributed as dist
+    from jepa_b200 import step as vj
+
+    def backward_once():
+        h = vj.forward_target(st["target"], clips, masks_pred)
+        z = st["encoder"](clips, masks_enc)
+        z = st["predictor"](z, h, masks_enc, masks_pred)
+        vj.jepa_loss(z, h).backward()
+        out = []
+        for net in (st["encoder"], st["predictor"]):
+            out.append(torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None]).clone())
+        st["optimizer"].zero_grad()
+        return torch.cat(out)
+
+    g_sync = backward_once()
+    stash = []
+    for net in (st["encoder"], st["predictor"]):
+        for m in net.modules():
+            if getattr(m, "_vj_grad_sync", None) is not None:
+                stash.append((m, m._vj_grad_sync))
+                m._vj_grad_sync = None
+    try:
+        g_local = backward_once()
+    finally:
+        for m, sy in stash:
+            m._vj_grad_sync = sy
+    g_mean = g_local.clone()
+    dist.all_reduce(g_mean, op=dist.ReduceOp.AVG)
+    torch.cuda.synchronize()
+    rel = float((g_sync - g_mean).norm() / g_mean.norm())
+    # the exchange must have DONE something: local and averaged gradients differ (different clips per rank)
+    spread = float((g_local - g_mean).norm() / g_mean.norm())
+    t = torch.tensor([rel, -spread], device=clips.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return dict(rel_l2_sync_vs_allreduce_mean=float(t[0]), rel_l2_local_vs_mean_min=float(-t[1]), n_synced_modules=len(stash),
+                n_grad_elements=int(g_mean.numel()))
 
 
 def ncu_gemm_traffic(cfg_name):
@@ -233,16 +283,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ddp_check = None
+    if world > 1 and not args.profile:
+        ddp_check = ddp_gradient_check(st, clips, me_d, mp_d)
+        if not (ddp_check["rel_l2_sync_vs_allreduce_mean"] < 1e-4 and ddp_check["rel_l2_local_vs_mean_min"] > 1e-3):
+            raise SystemExit(f"DDP gradient exchange check failed: {ddp_check}")
+
+    # `--dynamic-masks`: a NEW collator call every step (Ke / Kp change: tensor maps re-encoded, allocator sees new shapes)
+    dyn = None
+    if args.dynamic_masks:
+        from src.masks.multiblock3d import MaskCollator
+        torch.manual_seed(0)
+        coll = MaskCollator(cfgs_mask=VITL16_MASKS, crop_size=crop, num_frames=frames, patch_size=16, tubelet_size=2)
+        dummy = [torch.zeros(1) for _ in range(B)]
+
+        def dyn():
+            _, a, b = coll(dummy)
+            return [m.to(device, non_blocking=True) for m in a], [m.to(device, non_blocking=True) for m in b]
+
+    def step_masks():
+        return dyn() if dyn is not None else (me_d, mp_d)
+
     # ---- device-resident timing ("value") -------------------------------------------------------------
     for _ in range(args.warmup):
-        train_step(st, clips, me_d, mp_d)
+        train_step(st, clips, *step_masks(), loggers=args.loggers)
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.vj_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = train_step(st, clips, me_d, mp_d)
+        loss = train_step(st, clips, *step_masks(), loggers=args.loggers)
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -275,20 +346,34 @@ def run_ours(args):
         gemm_events.append((s, e, 2.0 * M * Nn * Kk))
         return r
 
+    attn_events = []
+    orig_af, orig_ab = Kn.attn_fwd, Kn.attn_bwd
+
+    def timed_attn(fn, mult):
+        def f(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **kw)
+            e.record()
+            attn_events.append((s, e, mult))
+            return r
+        return f
+
     roof_steps = 2
     Kn.gemm = timed_gemm
-    import jepa_b200.engine as eng
-    eng.K.gemm = timed_gemm
+    Kn.attn_fwd, Kn.attn_bwd = timed_attn(orig_af, 1), timed_attn(orig_ab, 2)
     try:
         for _ in range(roof_steps):
             train_step(st, clips, me_d, mp_d)
         torch.cuda.synchronize()
     finally:
         Kn.gemm = orig_gemm
-        eng.K.gemm = orig_gemm
+        Kn.attn_fwd, Kn.attn_bwd = orig_af, orig_ab
     gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
     gemm_flops_exec = sum(f for _, _, f in gemm_events)
     n_gemm = len(gemm_events)
+    attn_fwd_ms = sum(s.elapsed_time(e) for s, e, m in attn_events if m == 1) / roof_steps
+    attn_bwd_ms = sum(s.elapsed_time(e) for s, e, m in attn_events if m == 2) / roof_steps
 
     # ---- end-to-end: host inputs every step, loss read back ---------------------------------------------
     copy_stream = torch.cuda.Stream(device=device)
@@ -310,7 +395,7 @@ def run_ours(args):
         for i in range(n):
             b = bufs[i % 2]
             torch.cuda.current_stream().wait_event(b["ready"])
-            l = train_step(st, b["clips"], b["me"], b["mp"])
+            l = train_step(st, b["clips"], b["me"], b["mp"], loggers=args.loggers)
             if i + 1 < n:
                 prefetch(i + 1)
             out = float(l)          # device -> host read of the step's result (4 bytes), syncs the step
@@ -332,9 +417,11 @@ def run_ours(args):
         peaks = measured_peaks()
         f_clip = flops_per_clip(D, L, N, Ke, Kp)
         fg_clip = gemm_flops_per_clip(D, L, N, Ke, Kp)
+        fa_clip = f_clip - fg_clip
         gemm_ms_step = gemm_ms / roof_steps
         achieved = fg_clip * B / (gemm_ms_step * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
+        step_tf = f_clip * B / (ms_step * 1e-3) / 1e12
         line = {
             "metric": "clips/sec ViT-L/16 16x224^2 synthetic V-JEPA pre-training step" if args.config == "vitl16"
                       else f"clips/sec {args.config} synthetic V-JEPA pre-training step",
@@ -350,16 +437,31 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "vj::gemm_kernel (all Linear / patch-embed GEMMs of a step)",
-                         "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                         "traffic": ncu_gemm_traffic(args.config), "traffic_unit": "DRAM bytes per step over the family's launches "
-                         "(dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_step_launches_final.csv)",
-                         "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                         "launches_per_step": n_gemm // roof_steps, "gemm_ms_per_step": round(gemm_ms_step, 3),
-                         "executed_tflop_per_step": round(gemm_flops_exec / roof_steps / 1e12, 3),
-                         "step_tflops": round(f_clip * B / (ms_step * 1e-3) / 1e12, 1),
-                         "step_frac": round(f_clip * B / (ms_step * 1e-3) / 1e12 / peak, 4)},
+            "roofline": {
+                "bound": "tensor", "scope": "whole train step (BASELINE metric: % tensor-pipe roofline of the step)",
+                "achieved": round(step_tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(step_tf / peak, 4),
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "frac_of_burst": round(step_tf / peaks["bf16_burst"], 4), "frac_of_nominal_2250": round(step_tf / 2250.0, 4),
+                "algorithmic_tflop_per_step": round(f_clip * B / 1e12, 3),
+                "dominant_kernel": {
+                    "kernel": "vj::gemm_kernel (all Linear / patch-embed GEMMs of a step)", "achieved": round(achieved, 1),
+                    "frac": round(achieved / peak, 4), "launches_per_step": n_gemm // roof_steps,
+                    "gemm_ms_per_step": round(gemm_ms_step, 3), "algorithmic_tflop_per_step": round(fg_clip * B / 1e12, 3),
+                    "executed_tflop_per_step": round(gemm_flops_exec / roof_steps / 1e12, 3),
+                    "timing": "CUDA events around every launch on the launching stream, 2 extra steps"},
+                "attention": {
+                    "kernel": "vj::attn_fwd/bwd kernels", "fwd_ms_per_step": round(attn_fwd_ms, 3),
+                    "bwd_ms_per_step": round(attn_bwd_ms, 3), "algorithmic_tflop_per_step": round(fa_clip * B / 1e12, 3),
+                    "achieved": round(fa_clip * B / ((attn_fwd_ms + attn_bwd_ms) * 1e-3) / 1e12, 1),
+                    "frac": round(fa_clip * B / ((attn_fwd_ms + attn_bwd_ms) * 1e-3) / 1e12 / peak, 4)},
+                "traffic": ncu_gemm_traffic(args.config),
+                "traffic_unit": "DRAM bytes per step over the GEMM family's launches (dram__bytes_read.sum + "
+                                "dram__bytes_write.sum, ncu launch list in profiles/)"},
         }
+        if ddp_check is not None:
+            line["ddp_check"] = ddp_check
+        if args.dynamic_masks or args.loggers:
+            line["config"]["variant"] = {"dynamic_masks": bool(args.dynamic_masks), "loggers": bool(args.loggers)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.config, budget_s=25.0)
         print(json.dumps(line), flush=True)
@@ -433,8 +535,37 @@ def usable_cores():
     return max(1, min(n, 64))   # torch intra-op scaling of this workload saturates well before 64 threads
 
 
+def reference_cpu_run(cfg_name, B, steps, warmup, cores, timeout=1500):
+    """The UNMODIFIED reference (baseline/_ref, tools/install_reference.sh) through its own app.vjepa.train.main on the
+    host cores: fp32 (CPU autocast / GradScaler disable themselves), AdamW + EMA + its loggers in the step, synthetic clips,
+    its own collator - SURVEY 8d's CPU baseline.  Runs in a subprocess (tools/ref_gpu.py --backend gloo) because the
+    repo's drop-in src/ and app/ packages carry the reference's module names.  None if baseline/_ref is absent."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "app")):
+        return None
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_gpu.py"), "bench", "--config", cfg_name, "--backend", "gloo",
+           "--batch", str(B), "--steps", str(steps), "--warmup", str(warmup), "--loggers", "on", "--threads", str(cores)]
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    env["MASTER_PORT"] = "29611"
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=tempfile.gettempdir(), env=env)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        out = json.loads(lines[-1]) if lines else None
+    except Exception:
+        return None
+    if not out or "unavailable" in out or out.get("gpu_ms_per_step_median", -1) <= 0:
+        return None
+    return out
+
+
 def cpu_baseline(cfg_name, budget_s=25.0):
     cores = usable_cores()
+    ref = reference_cpu_run(cfg_name, B=2, steps=2, warmup=1, cores=cores)   # ~3 steps of 5-10 s at ViT-L
+    if ref is not None:
+        return {"value": ref["clips_per_s"], "unit": "clips/s", "cores": cores, "kind": "reference", "adamw": True,
+                "sample": f"unmodified reference app.vjepa.train.main (baseline/_ref) on the host: 2 timed fp32 steps (+1 warm-up) "
+                          f"at batch 2 of {cfg_name}, median {ref['gpu_ms_per_step_median'] / 1e3:.2f} s/step by its own "
+                          f"wall-time column, AdamW/EMA/loggers in the step, {cores} torch threads"}
     torch.set_num_threads(cores)
     B = 1
     step = oracle_step_fn(cfg_name, B)
@@ -447,9 +578,9 @@ def cpu_baseline(cfg_name, budget_s=25.0):
         step()
         times.append(time.perf_counter() - t0)
     t = min(times) if times else t_first
-    return {"value": round(B / t, 4), "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{1 + len(times)} fp32 train step(s) of the CPU oracle (oracle/vjepa_oracle.py) at batch {B} of "
-                      f"{cfg_name}, best step {t:.2f}s, torch intra-op threads = {cores}"}
+    return {"value": round(B / t, 4), "unit": "clips/s", "cores": cores, "kind": "port", "adamw": False,
+            "sample": f"{1 + len(times)} fp32 train step(s) of the CPU oracle (oracle/vjepa_oracle.py; AdamW omitted) at batch {B} "
+                      f"of {cfg_name}, best step {t:.2f}s, torch intra-op threads = {cores}"}
 
 
 def run_reference(args):
@@ -457,32 +588,47 @@ def run_reference(args):
     if rank != 0:
         return
     cores = usable_cores()
-    torch.set_num_threads(cores)
     model_name, D, L, heads, crop, frames, Bcfg = CONFIGS[args.config]
-    B = 1
-    step = oracle_step_fn(args.config, B)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss = step()
-    dt = time.perf_counter() - t0
-    value = B * args.steps / dt
     N = (frames // 2) * (crop // 16) ** 2
-    me, mp = seeded_masks(crop, frames, Bcfg, seed=0)   # same masks as the GPU arm (see oracle_step_fn)
+    me, mp = seeded_masks(crop, frames, Bcfg, seed=0)
     Ke, Kp = [int(m.shape[1]) for m in me], [int(m.shape[1]) for m in mp]
-    sample = (f"each step = one fp32 train step of the CPU oracle port on {B} clip of {args.config} "
-              f"({model_name}, {frames}x{crop}x{crop}, masks Ke={Ke} Kp={Kp}); {cores} host threads")
+    B = 2
+    ref = reference_cpu_run(args.config, B=B, steps=args.steps, warmup=args.warmup, cores=cores)
+    if ref is not None:
+        kind, adamw = "reference", True
+        value = ref["clips_per_s"]
+        ms_step = ref["gpu_ms_per_step_median"]
+        loss = ref["losses"][-1]
+        sample = (f"each step = one fp32 train step of the UNMODIFIED reference (baseline/_ref, app.vjepa.train.main: target fwd, "
+                  f"context+predictor fwd/bwd, AdamW, EMA, its loggers) on {B} clips of {args.config} ({model_name}, "
+                  f"{frames}x{crop}x{crop}, its own MaskCollator at batch {B}); median of {args.steps} by its wall-time column; "
+                  f"{cores} host threads")
+    else:
+        kind, adamw = "port", False
+        torch.set_num_threads(cores)
+        B = 1
+        step = oracle_step_fn(args.config, B)
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            loss = step()
+        dt = time.perf_counter() - t0
+        value = B * args.steps / dt
+        ms_step = dt / args.steps * 1e3
+        sample = (f"baseline/_ref absent -> CPU oracle port: each step = one fp32 train step (AdamW omitted) on {B} clip of "
+                  f"{args.config} ({model_name}, {frames}x{crop}x{crop}, masks Ke={Ke} Kp={Kp}); {cores} host threads")
     line = {
         "impl": "reference",
         "metric": "clips/sec ViT-L/16 16x224^2 synthetic V-JEPA pre-training step" if args.config == "vitl16"
                   else f"clips/sec {args.config} synthetic V-JEPA pre-training step",
         "value": round(value, 4), "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(ms_step, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {model_name} 2x16x16 tubelets, {frames}x{crop}x{crop}, CPU sample batch {B} "
                                f"(GPU arm: batch {Bcfg}/GPU)", "global_batch": B, "parallelism": "cpu", "loss_last": loss},
-        "cpu_baseline": {"value": round(value, 4), "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": "clips/s", "cores": cores, "kind": kind, "adamw": adamw,
+                         "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -498,6 +644,8 @@ def main():
     ap.add_argument("--config", default="vitl16", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dynamic-masks", action="store_true", help="new collator call every step (SURVEY 8d second run)")
+    ap.add_argument("--loggers", action="store_true", help="as-shipped step: grad_logger x2 + adamw_logger inside the step")
     ap.add_argument("--profile", action="store_true", help="bare steps only (for ncu); never a bench value")
     args = ap.parse_args()
     if args.impl == "reference":

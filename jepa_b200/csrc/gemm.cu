@@ -565,7 +565,9 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   VJ_CHECK_ARG(A && B && D, "vj_gemm: null operand");
   VJ_CHECK_ARG(M > 0 && N > 0 && K > 0, "vj_gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VJ_CHECK_ARG(N % 64 == 0, "vj_gemm: N=%d must be a multiple of 64", N);
-  VJ_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "vj_gemm: K/lda/ldb must be multiples of 8");
+  // TMA needs 16-byte row strides; the reduction extent itself is free (tails are zero-filled by TMA): for MN-major
+  // operands (wgrad: K = token count) K is the OUTER dimension and may be any positive number.
+  VJ_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "vj_gemm: lda/ldb must be multiples of 8 elements (16-byte rows)");
   VJ_CHECK_ARG(ldd % (d_f32 ? 4 : 8) == 0, "vj_gemm: ldd misaligned");
   VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(D) & 15) == 0,

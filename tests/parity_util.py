@@ -16,25 +16,47 @@ def c1_masks(batch):
     return [m[:batch].clone() for m in g["enc"]], [m[:batch].clone() for m in g["pred"]]
 
 
-def _shapes(depth, pred_depth):
-    """state-dict shapes of the C1 networks (optionally shallower), derived from the product modules on CPU."""
+# 2-block slices of the BASELINE networks: full width / heads / sequence lengths of ViT-L/16 and
+# ViT-H/16 at 16x224^2, one clip, the C2 / C4 seeded masks (first collator call at the config's batch size, first row)
+VITL_2B = dict(model_name='vit_large', crop_size=224, patch_size=16, num_frames=16, tubelet_size=2, batch=1,
+               pred_depth=2, pred_embed_dim=384, depth=2, heads=16, embed_dim=1024, mask_batch=32)
+VITH_2B = dict(model_name='vit_huge', crop_size=224, patch_size=16, num_frames=16, tubelet_size=2, batch=1,
+               pred_depth=2, pred_embed_dim=384, depth=2, heads=16, embed_dim=1280, mask_batch=24)
+
+
+def cfg_masks(cfg, batch):
+    """Masks of a step config: C1 -> the committed reference-generated fixture; others -> the (bit-exact, sha-pinned)
+    product collator seeded like BASELINE.md section 2, first `batch` rows."""
+    if cfg is C1:
+        return c1_masks(batch)
+    from common import VITL16_MASKS
+    from jepa_b200.masks import MultiBlock3DMaskCollator as MaskCollator
+    torch.manual_seed(0)
+    coll = MaskCollator(cfgs_mask=VITL16_MASKS, crop_size=cfg["crop_size"], num_frames=cfg["num_frames"],
+                        patch_size=cfg["patch_size"], tubelet_size=cfg["tubelet_size"])
+    _, me, mp = coll([torch.zeros(1) for _ in range(cfg["mask_batch"])])
+    return [m[:batch].clone() for m in me], [m[:batch].clone() for m in mp]
+
+
+def _shapes(depth, pred_depth, cfg=C1):
+    """state-dict shapes of the networks (optionally shallower), derived from the product modules on CPU."""
     from jepa_b200.models import VisionTransformer, vit_predictor
     from functools import partial
     import torch.nn as nn
-    enc = VisionTransformer(img_size=C1["crop_size"], patch_size=C1["patch_size"], num_frames=C1["num_frames"],
-                            tubelet_size=C1["tubelet_size"], embed_dim=C1["embed_dim"], depth=depth, num_heads=C1["heads"],
+    enc = VisionTransformer(img_size=cfg["crop_size"], patch_size=cfg["patch_size"], num_frames=cfg["num_frames"],
+                            tubelet_size=cfg["tubelet_size"], embed_dim=cfg["embed_dim"], depth=depth, num_heads=cfg["heads"],
                             mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), uniform_power=True)
-    pred = vit_predictor(img_size=C1["crop_size"], use_mask_tokens=True, patch_size=C1["patch_size"],
-                         num_frames=C1["num_frames"], tubelet_size=C1["tubelet_size"], embed_dim=C1["embed_dim"],
-                         predictor_embed_dim=C1["pred_embed_dim"], depth=pred_depth, num_heads=C1["heads"],
+    pred = vit_predictor(img_size=cfg["crop_size"], use_mask_tokens=True, patch_size=cfg["patch_size"],
+                         num_frames=cfg["num_frames"], tubelet_size=cfg["tubelet_size"], embed_dim=cfg["embed_dim"],
+                         predictor_embed_dim=cfg["pred_embed_dim"], depth=pred_depth, num_heads=cfg["heads"],
                          uniform_power=True, num_mask_tokens=2, zero_init_mask_tokens=True)
     return enc, pred
 
 
-def build_states(depth_limit=None):
-    depth = depth_limit or C1["depth"]
-    pdepth = depth_limit or C1["pred_depth"]
-    enc, pred = _shapes(depth, pdepth)
+def build_states(depth_limit=None, cfg=C1):
+    depth = depth_limit or cfg["depth"]
+    pdepth = depth_limit or cfg["pred_depth"]
+    enc, pred = _shapes(depth, pdepth, cfg)
     enc_shapes = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
     pred_shapes = {k: tuple(v.shape) for k, v in pred.state_dict().items()}
     s_enc = synth_state(enc_shapes, seed=11, keep=("pos_embed",))
@@ -43,10 +65,12 @@ def build_states(depth_limit=None):
     return enc, pred, s_enc, s_pred, s_tgt, depth, pdepth
 
 
-def run_c1_step_cuda(device, batch=C1["batch"], depth_limit=None):
+def run_c1_step_cuda(device, batch=None, depth_limit=None, cfg=C1):
     from jepa_b200 import step as vj
     from jepa_b200.models import MultiMaskWrapper, PredictorMultiMaskWrapper
-    enc, pred, s_enc, s_pred, s_tgt, depth, pdepth = build_states(depth_limit)
+    C1 = cfg
+    batch = batch or cfg["batch"]
+    enc, pred, s_enc, s_pred, s_tgt, depth, pdepth = build_states(depth_limit, cfg)
     enc.load_state_dict(s_enc, strict=False)
     pred.load_state_dict(s_pred, strict=False)
     tgt = copy.deepcopy(enc)
@@ -55,7 +79,7 @@ def run_c1_step_cuda(device, batch=C1["batch"], depth_limit=None):
     for p in tgt.parameters():
         p.requires_grad = False
     clips = synth_clips(batch, C1["num_frames"], C1["crop_size"], C1["crop_size"], seed=0).to(device)
-    me, mp = c1_masks(batch)
+    me, mp = cfg_masks(cfg, batch)
     me, mp = [m.to(device) for m in me], [m.to(device) for m in mp]
 
     h = vj.forward_target(tgt, clips, mp)
@@ -76,10 +100,12 @@ def run_c1_step_cuda(device, batch=C1["batch"], depth_limit=None):
     return out
 
 
-def run_c1_step_oracle(batch=C1["batch"], depth_limit=None, dtype=torch.float32):
+def run_c1_step_oracle(batch=None, depth_limit=None, dtype=torch.float32, cfg=C1):
     from oracle import vjepa_oracle as O
-    _, _, s_enc, s_pred, s_tgt, depth, pdepth = build_states(depth_limit)
-    enc_mod, pred_mod = _shapes(depth, pdepth)
+    C1 = cfg
+    batch = batch or cfg["batch"]
+    _, _, s_enc, s_pred, s_tgt, depth, pdepth = build_states(depth_limit, cfg)
+    enc_mod, pred_mod = _shapes(depth, pdepth, cfg)
 
     def with_pos(state, mod, key):
         full = {k: v.clone().to(dtype) for k, v in state.items()}
@@ -94,7 +120,7 @@ def run_c1_step_oracle(batch=C1["batch"], depth_limit=None, dtype=torch.float32)
             if k != frozen:
                 v.requires_grad_(True)
     clips = synth_clips(batch, C1["num_frames"], C1["crop_size"], C1["crop_size"], seed=0).to(dtype)
-    me, mp = c1_masks(batch)
+    me, mp = cfg_masks(cfg, batch)
     heads = C1["heads"]
     h = O.forward_target(S_tgt, clips, mp, depth, heads)
     z_enc = [O.encoder(S_enc, clips, [m], depth, heads) for m in me]

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from common import synth_clips
-from parity_util import (TOL_ACT, c1_masks, compare_step, rel_l2, run_c1_step_cuda, run_c1_step_oracle)
+from parity_util import (TOL_ACT, VITH_2B, VITL_2B, c1_masks, compare_step, rel_l2, run_c1_step_cuda, run_c1_step_oracle)
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -183,17 +183,27 @@ def test_patch_embed_matches_oracle(dev):
     assert torch.equal(outk.view(B, Kk, D), Kn.gather_rows(out.view(B, 784, D), m))
 
 
-@pytest.mark.parametrize("H,hd,lens", [(3, 64, [208, 160]), (16, 24, [296, 40, 128]), (3, 128, [200, 72]),
-                                       (4, 80, [300, 100])])
-def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
-    """Attention (modules.py:61-78 core) incl. the zero-padded heads (predictor hd=24 -> 32, ViT-H hd=80 -> 128),
-    ragged sequence tails."""
+def _attention_case(dev, H, hd, lens, late_max=False, backward=True, seed=None):
+    """Attention (modules.py:61-78 core) vs an fp64 softmax on the host, incl. the zero-padded heads (predictor hd=24 ->
+    32, ViT-H hd=80 -> 128) and ragged sequence tails.  late_max: a few keys far into the sequence (past KV tile 8) score
+    ~2^6..2^12 times above everything before them for some query rows, so the forward's lazy rescale (reference max moved
+    only when it grows by more than 2^8) fires late and repeatedly."""
     from jepa_b200 import kernels as Kn
     from jepa_b200.params import padded_head_dim
     hdp = padded_head_dim(hd)
     T = sum(lens)
-    g = torch.Generator().manual_seed(hd)
+    g = torch.Generator().manual_seed(hd if seed is None else seed)
     q, k, v, do = (bf(torch.randn(T, H, hd, generator=g)) for _ in range(4))
+    if late_max:
+        off = 0
+        for L in lens:
+            for frac, gain in ((0.70, 3.0), (0.83, 6.0), (0.97, 9.0)):
+                kpos = off + int(frac * L)
+                rows = torch.arange(off + 5, off + L, 7)      # every 7th query row sees the spike
+                qdir = q[rows].mean(0)                          # [H, hd]
+                k[kpos] = bf(gain * qdir / qdir.norm(dim=-1, keepdim=True) * (hd ** 0.5))
+                q[rows] = bf(q[rows] + 2.0 * qdir / qdir.norm(dim=-1, keepdim=True))
+            off += L
     qkv = torch.zeros(T, 3, H, hdp)
     qkv[:, 0, :, :hd], qkv[:, 1, :, :hd], qkv[:, 2, :, :hd] = q, k, v
     dop = torch.zeros(T, H, hdp)
@@ -204,29 +214,62 @@ def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
     lse = torch.empty(H, T, device=dev)
     scale = hd ** -0.5
     Kn.attn_fwd(qkv_d, out, lse, cu, len(lens), max(lens), H, hdp, scale)
-    dqkv = torch.empty_like(qkv_d)
-    # hd <= 32 exercises the fused dQ path (TMA reduce-add of per-key-tile partials), the others the two-kernel path
-    ws = torch.empty(T, H * hdp, device=dev) if hdp <= 32 else None
-    Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dqkv, cu,
-                len(lens), max(lens), H, hdp, scale, dq_acc_ws=ws)
-    if ws is not None:   # and both paths agree
-        dq2 = torch.empty_like(qkv_d)
-        Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dq2,
-                    cu, len(lens), max(lens), H, hdp, scale)
-        close_bf16(dqkv, dq2.float().cpu(), atol=2e-2, rtol=2e-2)
-    out_c, dq_c = out.float().cpu().view(T, H, hdp), dqkv.float().cpu().view(T, 3, H, hdp)
+    out_c = out.float().cpu().view(T, H, hdp)
+    dq_c = None
+    if backward:
+        dqkv = torch.empty_like(qkv_d)
+        # hd <= 32 exercises the fused dQ path (TMA reduce-add of per-key-tile partials), the others the two-kernel path
+        ws = torch.empty(T, H * hdp, device=dev) if hdp <= 32 else None
+        Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev), dqkv,
+                    cu, len(lens), max(lens), H, hdp, scale, dq_acc_ws=ws)
+        if ws is not None:   # and both paths agree
+            dq2 = torch.empty_like(qkv_d)
+            Kn.attn_bwd(qkv_d, out, dop.reshape(T, H * hdp).to(dev, torch.bfloat16), lse, torch.empty(H * T, device=dev),
+                        dq2, cu, len(lens), max(lens), H, hdp, scale)
+            close_bf16(dqkv, dq2.float().cpu(), atol=2e-2, rtol=2e-2)
+        dq_c = dqkv.float().cpu().view(T, 3, H, hdp)
     if hdp > hd:  # padded lanes stay exactly zero end to end
-        assert float(out_c[..., hd:].abs().max()) == 0 and float(dq_c[..., hd:].abs().max()) == 0
+        assert float(out_c[..., hd:].abs().max()) == 0
+        assert dq_c is None or float(dq_c[..., hd:].abs().max()) == 0
+    lse_c = lse.cpu()
     off = 0
     for L in lens:
-        qq, kk, vv = (t[off:off + L].double().transpose(0, 1).requires_grad_(True) for t in (q, k, v))  # [H, L, hd]
-        att = torch.softmax((qq @ kk.transpose(-2, -1)) * scale, dim=-1)
+        qq, kk, vv = (t[off:off + L].double().transpose(0, 1).requires_grad_(backward) for t in (q, k, v))  # [H, L, hd]
+        sc = (qq @ kk.transpose(-2, -1)) * scale
+        att = torch.softmax(sc, dim=-1)
         o = att @ vv
-        o.backward(do[off:off + L].double().transpose(0, 1))
         close_bf16(out_c[off:off + L, :, :hd], o.detach().transpose(0, 1).float())
-        for i, t in enumerate((qq, kk, vv)):
-            close_bf16(dq_c[off:off + L, i, :, :hd], t.grad.transpose(0, 1).float(), atol=3e-2, rtol=2e-2)
+        # log2-domain LSE saved for the backward
+        ref_lse2 = torch.logsumexp(sc.detach(), dim=-1) * 1.4426950408889634
+        assert float((lse_c[:, off:off + L].double() - ref_lse2).abs().max()) < 2e-2
+        if backward:
+            o.backward(do[off:off + L].double().transpose(0, 1))
+            for i, t in enumerate((qq, kk, vv)):
+                close_bf16(dq_c[off:off + L, i, :, :hd], t.grad.transpose(0, 1).float(), atol=3e-2, rtol=2e-2)
         off += L
+
+
+@pytest.mark.parametrize("H,hd,lens", [(3, 64, [208, 160]), (16, 24, [296, 40, 128]), (3, 128, [200, 72]),
+                                       (4, 80, [300, 100])])
+def test_attention_fwd_bwd_vs_oracle(dev, H, hd, lens):
+    _attention_case(dev, H, hd, lens)
+
+
+# BASELINE sequence lengths: target 1568 = 12x128+32 (13 KV tiles), predictor 1184 / 1192 (hd 24 ->
+# 32, fused dQ), context 360 / 48, ViT-H hd 80 -> 128, C5 context 1512 / 288 and predictor 3680 / 3600.
+@pytest.mark.parametrize("H,hd,lens,late", [
+    (2, 64, [1568], False), (2, 64, [1568], True), (2, 64, [360, 48, 360], False),
+    (2, 24, [1184, 1192], False), (2, 24, [1192, 1184], True),
+    (2, 80, [1568], False), (1, 80, [1568, 360, 48], True), (1, 80, [1512, 288], False), (1, 24, [3680, 3600], False),
+])
+def test_attention_baseline_shapes_vs_fp64(dev, H, hd, lens, late):
+    _attention_case(dev, H, hd, lens, late_max=late, seed=hd + len(lens) + int(late))
+
+
+@pytest.mark.parametrize("late", [False, True])
+def test_attention_c5_long_sequence_forward(dev, late):
+    """C5 target pass: S = 4608 (36 KV tiles), hd 80 -> 128, forward only (the target encoder has no backward)."""
+    _attention_case(dev, 1, 80, [4608], late_max=late, backward=False, seed=7)
 
 
 def test_target_ln_gather_and_loss(dev):
@@ -333,6 +376,66 @@ def test_c1_step_full_vs_oracle_and_golden(dev, golden_dir):
             assert abs(float(got[f"{key}_grad"][n].norm()) - refn) <= 6e-2 * refn + 1e-9, n
     for n, ref_slice in gold["ema_slices"].items():
         assert torch.equal(got["ema"][n].reshape(-1)[:32], ref_slice), n
+
+
+@pytest.mark.parametrize("cfg", [VITL_2B, VITH_2B], ids=["vitl16_2blocks", "vith16_2blocks"])
+def test_baseline_width_step_vs_oracle(dev, cfg):
+    """a 2+2-block slice of the BASELINE networks at FULL width / heads / sequence lengths (ViT-L: D=1024,
+    16 heads of 64; ViT-H: D=1280, 16 heads of 80 -> 128; predictor 384 / 16 heads of 24 -> 32; N=1568 target tokens,
+    C2's seeded masks Ke=[360,48] Kp=[824,1144]), one clip, against the fp32 CPU oracle: target / context / predictor
+    outputs, loss, every parameter gradient (BN=256 GEMM tiles, split-K wgrads at these K), EMA bit-exact."""
+    got = run_c1_step_cuda(dev, cfg=cfg)
+    ref = run_c1_step_oracle(cfg=cfg)
+    assert [tuple(t.shape[1:]) for t in got["z"]] == [(824, cfg["embed_dim"]), (1144, cfg["embed_dim"])]
+    compare_step(got, ref, verbose=True)
+
+
+@pytest.mark.parametrize("T,n_out,k_in", [(13056, 4096, 1024), (76032, 1536, 384), (76032, 384, 1536), (50176 + 24, 1024, 1024)])
+def test_wgrad_split_k_full_token_counts(dev, T, n_out, k_in):
+    """wgrad GEMMs at the C2 token counts (context 13 056, predictor 76 032 rows; one count that is not a multiple of 64)
+    with the engine's own split-K choice, fp32 reduce-add into a non-zero buffer, vs fp64 on a 256 x 256 output slice."""
+    from jepa_b200 import kernels as Kn
+    from jepa_b200.engine import _split_k_for
+    g = torch.Generator().manual_seed(T % 997)
+    dy = bf(torch.randn(T, n_out, generator=g))
+    x = bf(torch.randn(T, k_in, generator=g) * 0.5)
+    base = torch.randn(n_out, k_in, generator=g)
+    dw = base.clone().to(dev)
+    sk = _split_k_for(n_out, k_in, T)
+    Kn.gemm(dy.to(dev, torch.bfloat16), x.to(dev, torch.bfloat16), dw, a_mn=True, b_mn=True, accumulate=True, split_k=sk)
+    r0, c0 = n_out - 256, max(0, k_in - 256 - 64)
+    ref = base[r0:r0 + 256, c0:c0 + 256].double() + dy[:, r0:r0 + 256].double().t() @ x[:, c0:c0 + 256].double()
+    got = dw[r0:r0 + 256, c0:c0 + 256].cpu()
+    assert rel_l2(got, ref) < 2e-6, (sk, rel_l2(got, ref))
+    db = torch.zeros(n_out, device=dev)
+    Kn.colsum(dy.to(dev, torch.bfloat16), db)
+    assert rel_l2(db.cpu(), dy.double().sum(0)) < 1e-5
+
+
+def test_step_with_token_counts_not_multiple_of_8(dev):
+    """Image-like / odd-batch settings give B*sum(K_i) % 8 != 0: the wgrad GEMMs reduce over the token count, which
+    only has to be positive.  One ViT-Tiny encoder fwd+bwd over masks keeping 21 and 13 tokens of 3 clips vs the oracle."""
+    from jepa_b200.models import vit_tiny
+    from oracle import vjepa_oracle as O
+    torch.manual_seed(0)
+    enc = vit_tiny(img_size=224, patch_size=16, num_frames=8, tubelet_size=2, uniform_power=True).to(dev)
+    clips = synth_clips(3, 8, 224, 224, seed=5)
+    g = torch.Generator().manual_seed(2)
+    masks = [torch.stack([torch.randperm(784, generator=g)[:k].sort().values for _ in range(3)]) for k in (21, 13)]
+    outs = enc.forward_multi(clips.to(dev), [m.to(dev) for m in masks])
+    w = [torch.randn(o.shape, generator=g) for o in outs]
+    sum((o.float() * wi.to(dev)).sum() for o, wi in zip(outs, w)).backward()
+    S = {k: v.detach().float().cpu().clone() for k, v in enc.state_dict().items()}
+    for k, v in S.items():
+        if k != "pos_embed":
+            v.requires_grad_(True)
+    ref = [O.encoder(S, clips, [m], 12, 3) for m in masks]
+    sum((o * wi).sum() for o, wi in zip(ref, w)).backward()
+    for o, r in zip(outs, ref):
+        assert rel_l2(o.detach().float().cpu(), r.detach()) < TOL_ACT
+    for n, p in enc.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad.float().cpu(), S[n].grad) < 3e-2, n
 
 
 def test_multimask_fused_equals_per_mask_calls(dev):
