@@ -288,8 +288,8 @@ def main(args, resume_preempt=False):
                 scaler.scale(loss).backward()
                 scaler.unscale_(optimizer)
                 if (epoch > warmup) and (clip_grad is not None):
-                    _enc_norm = torch.nn.utils.clip_grad_norm_(encoder.parameters(), clip_grad)
-                    _pred_norm = torch.nn.utils.clip_grad_norm_(predictor.parameters(), clip_grad)
+                    _enc_norm = vj.clip_grad_norm_(encoder, clip_grad)
+                    _pred_norm = vj.clip_grad_norm_(predictor, clip_grad)
                 scaler.step(optimizer)
                 scaler.update()
                 grad_stats = grad_logger(encoder.named_parameters())

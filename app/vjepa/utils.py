@@ -6,7 +6,7 @@ import torch
 
 import src.models.predictor as vit_pred
 import src.models.vision_transformer as video_vit
-from jepa_b200.optim import FlatAdamW
+from jepa_b200.optim import FlatAdamW, FlatGradScaler
 from src.models.utils.multimask import MultiMaskWrapper, PredictorMultiMaskWrapper
 from src.utils.schedulers import CosineWDSchedule, WarmupCosineSchedule
 from src.utils.tensors import trunc_normal_
@@ -104,5 +104,5 @@ def init_opt(encoder, predictor, iterations_per_epoch, start_lr, ref_lr, warmup,
     scheduler = WarmupCosineSchedule(optimizer, warmup_steps=int(warmup * iterations_per_epoch), start_lr=start_lr,
                                      ref_lr=ref_lr, final_lr=final_lr, T_max=total)
     wd_scheduler = CosineWDSchedule(optimizer, ref_wd=wd, final_wd=final_wd, T_max=total)
-    scaler = torch.cuda.amp.GradScaler() if mixed_precision else None
+    scaler = FlatGradScaler() if mixed_precision else None   # torch.cuda.amp.GradScaler with a fused flat-buffer unscale
     return optimizer, scaler, scheduler, wd_scheduler

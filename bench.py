@@ -312,8 +312,10 @@ def run_ours(args):
     launches0 = lib.vj_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         loss = train_step(st, clips, *step_masks(), loggers=args.loggers)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # host time to ENQUEUE a step (no sync inside)
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -437,6 +439,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": round(host_enqueue_ms, 2),
             "roofline": {
                 "bound": "tensor", "scope": "whole train step (BASELINE metric: % tensor-pipe roofline of the step)",
                 "achieved": round(step_tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(step_tf / peak, 4),

@@ -145,9 +145,31 @@ int vj_adamw_step(float* p, const float* g, float* m, float* v, long long n, flo
                   void* stream);
 /* AdamW over a whole flat parameter buffer in one launch: group_ids (device uint8 per 64-element block)
  * select lr / weight decay from the 4-entry HOST tables lr4 / wd4; id 255 = frozen or padding (skipped). */
+/* step_dev (device fp32 scalar, nullable): when given the step count is read from (and, unless found_inf, advanced on) the
+ * device, so a GradScaler-skipped step does not advance the bias correction (torch's fused/capturable AdamW semantics;
+ * `step` is then ignored).  shadow_bf16 (nullable, n elements): bf16 copy of the updated parameters written in the same
+ * pass - the tensor-core operands of the next step (replaces the separate vj_cast_f32_bf16 pass). */
 int vj_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned char* group_ids, long long n,
                   const float* lr4, const float* wd4, float beta1, float beta2, float eps, int step,
-                  const float* inv_scale_dev, const float* found_inf_dev, void* stream);
+                  const float* inv_scale_dev, const float* found_inf_dev, float* step_dev, void* shadow_bf16, void* stream);
+/* vj_ema_update that also writes the bf16 shadow of the updated k (target-encoder weights of the next step). */
+int vj_ema_update_shadow(float* k, const float* q, long long n, float m, float one_minus_m, void* shadow_bf16, void* stream);
+
+/* ---- segmented statistics over flat gradient / moment buffers (logging + clipping without host syncs) ------------
+ * seg: device uint16 per 64-element block of the flat buffer = parameter-tensor id, 0xFFFF = skip (frozen / padding).
+ * vj_grad_unscale_stats: one pass over the flat gradient buffer: g *= *inv_scale_dev (if given; written back iff
+ * write_back), *found_inf_dev = 1 if any value is non-finite, sumsq_out[id] += sum of squares of tensor id.
+ * Replaces torch._amp_foreach_non_finite_check_and_unscale_ behind scaler.unscale_ (app/vjepa/train.py:463) and the
+ * per-tensor torch.norm loop of grad_logger (src/utils/logging.py:91-105). */
+int vj_grad_unscale_stats(float* g, const unsigned short* seg, long long n, const float* inv_scale_dev,
+                          float* found_inf_dev, float* sumsq_out, int write_back, void* stream);
+/* out[id] += sum |x| over tensor id  (adamw_logger's exp_avg.abs().mean() / exp_avg_sq.abs().mean(), logging.py:108-118). */
+int vj_seg_abs_sum(const float* x, const unsigned short* seg, long long n, float* out, void* stream);
+/* total_norm = sqrt(sum sumsq[0..n_seg)), coef = min(1, max_norm / (total_norm + 1e-6)), both device scalars
+ * (torch.nn.utils.clip_grad_norm_, app/vjepa/train.py:468-471). */
+int vj_clip_coef(const float* sumsq, int n_seg, float max_norm, float* total_norm_out, float* coef_out, void* stream);
+/* x *= *coef_dev when *coef_dev < 1 (no memory traffic otherwise). */
+int vj_scale_flat(float* x, long long n, const float* coef_dev, void* stream);
 /* out[0] += sum(x^2) over a flat fp32 buffer (grad-norm statistics, src/utils/logging.py:91-105). */
 int vj_sumsq(const float* x, long long n, float* out, void* stream);
 

@@ -37,7 +37,12 @@ SIGNATURES = {
     "vj_head_pad": (I, [P, I, P, I, L, I, I, I, L, I, P]),
     "vj_ema_update": (I, [P, P, L, F, F, P]),
     "vj_adamw_step": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P, P]),
-    "vj_adamw_flat": (I, [P, P, P, P, P, L, P, P, F, F, F, I, P, P, P]),
+    "vj_adamw_flat": (I, [P, P, P, P, P, L, P, P, F, F, F, I, P, P, P, P, P]),
+    "vj_ema_update_shadow": (I, [P, P, L, F, F, P, P]),
+    "vj_grad_unscale_stats": (I, [P, P, L, P, P, P, I, P]),
+    "vj_seg_abs_sum": (I, [P, P, L, P, P]),
+    "vj_clip_coef": (I, [P, I, F, P, P, P]),
+    "vj_scale_flat": (I, [P, L, P, P]),
     "vj_sumsq": (I, [P, L, P, P]),
 }
 

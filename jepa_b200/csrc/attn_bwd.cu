@@ -12,6 +12,8 @@
 //   attn_bwd_dq_kernel : one CTA per 128-query tile, loops over key tiles; dQ += dS K in TMEM.
 // P is recomputed from the forward's log2-domain LSE.  Same qkv / O layouts as attn_fwd.cu; the
 // gradient dqkv has the qkv layout [T, 3*H*HD] so the qkv wgrad/dgrad GEMMs consume it directly.
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "vjepa_b200.h"
 
@@ -46,38 +48,6 @@ struct BwdCfg {
 };
 
 VJ_DEVINL void named_bar_sync_attn(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// write 8 packed bf16 (16 bytes) of row r, 16-byte column chunk col8 (0..15) into a [128x128] K-major tile
-VJ_DEVINL void ptile_store(uint32_t tile, int r, int col8, const uint4& u) {
-  sts128(tile + (col8 >> 3) * 16384 + r * 128 + (((col8 & 7) ^ (r & 7)) << 4), u);
-}
-
-// coalesced store of a per-warp staged [32 rows x HD] bf16 block to global rows
-template <int HD>
-VJ_DEVINL void store_rows_bf16(uint32_t stage, const float (&vals)[HD], float mul, int lane, __nv_bfloat16* gbase,
-                               long long ld, int row_first, int rows_valid) {
-  constexpr int ORB = HD * 2, CH = ORB / 16, ROWS_PER_IT = 32 / CH;
-#pragma unroll
-  for (int g = 0; g < CH; ++g) {
-    uint4 u;
-    u.x = pack_bf16x2(vals[8 * g + 0] * mul, vals[8 * g + 1] * mul);
-    u.y = pack_bf16x2(vals[8 * g + 2] * mul, vals[8 * g + 3] * mul);
-    u.z = pack_bf16x2(vals[8 * g + 4] * mul, vals[8 * g + 5] * mul);
-    u.w = pack_bf16x2(vals[8 * g + 6] * mul, vals[8 * g + 7] * mul);
-    sts128(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4), u);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < CH; ++it) {
-    const int rr = it * ROWS_PER_IT + lane / CH;
-    const int g = lane % CH;
-    if (rr < rows_valid) {
-      const uint4 u = lds128(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase) + ((long long)(row_first + rr) * ld) * 2 + g * 16) = u;
-    }
-  }
-  __syncwarp();
-}
 
 // ---------------------------------------------------------------------------------------------
 // delta[h, t] = sum_d dO[t, h*HD + d] * O[t, h*HD + d]
@@ -589,6 +559,43 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float4* __re
   }
 }
 
+int launch_attn_delta(const void* out, const void* dout, float* delta, int T, int H, int HD, cudaStream_t s) {
+  int g = (T + 7) / 8;
+  const int cap = num_sms() * 8;
+  if (g > cap) g = cap;
+  attn_delta_kernel<<<g, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout),
+                                      delta, T, H, HD);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}
+
+int launch_attn_dq_convert(const float* dq_acc, void* dqkv, long long T, int HHD, float scale, cudaStream_t s) {
+  long long n4 = T * HHD / 4;
+  long long g = (n4 + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  attn_dq_convert_kernel<<<int(g), 256, 0, s>>>(reinterpret_cast<const float4*>(dq_acc), reinterpret_cast<__nv_bfloat16*>(dqkv), T,
+                                                HHD, scale);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}
+
+// second-generation fused backward for head dims <= 32 (attn_bwd2.cu)
+template <int HD>
+int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
+                     float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale, cudaStream_t s);
+
+// VJ_ATTN_BWD=1 selects the first-generation kernels for every head dim (A/B timing)
+static int attn_bwd_generation() {
+  static int gen = -1;
+  if (gen < 0) {
+    const char* e = getenv("VJ_ATTN_BWD");
+    gen = (e && e[0] == '1') ? 1 : 2;
+  }
+  return gen;
+}
+
 template <int HD>
 static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
                            void* dqkv, float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale,
@@ -659,6 +666,8 @@ extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, c
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   VJ_CHECK_ARG(qkv && out && dout && lse2 && delta_ws && dqkv && cu_seqlens, "vj_attn_bwd: null pointer");
   VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_bwd: empty problem");
+  if (HD == 32 && dq_acc_ws != nullptr && attn_bwd_generation() == 2)
+    return launch_attn_bwd2<32>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
   switch (HD) {
     case 32: return launch_attn_bwd<32>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
     case 64: return launch_attn_bwd<64>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);

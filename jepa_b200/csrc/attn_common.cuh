@@ -48,4 +48,37 @@ VJ_DEVINL uint64_t ptile_desc(uint32_t tile, int kk) {
 }
 
 
+// write 8 packed bf16 (16 bytes) of row r, 16-byte column chunk col8 (0..15) into a [128x128] K-major tile
+VJ_DEVINL void ptile_store(uint32_t tile, int r, int col8, const uint4& u) {
+  sts128(tile + (col8 >> 3) * 16384 + r * 128 + (((col8 & 7) ^ (r & 7)) << 4), u);
+}
+
+// coalesced store of a per-warp staged [32 rows x HD] bf16 block to global rows
+template <int HD>
+VJ_DEVINL void store_rows_bf16(uint32_t stage, const float (&vals)[HD], float mul, int lane, __nv_bfloat16* gbase,
+                               long long ld, int row_first, int rows_valid) {
+  constexpr int ORB = HD * 2, CH = ORB / 16, ROWS_PER_IT = 32 / CH;
+#pragma unroll
+  for (int g = 0; g < CH; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(vals[8 * g + 0] * mul, vals[8 * g + 1] * mul);
+    u.y = pack_bf16x2(vals[8 * g + 2] * mul, vals[8 * g + 3] * mul);
+    u.z = pack_bf16x2(vals[8 * g + 4] * mul, vals[8 * g + 5] * mul);
+    u.w = pack_bf16x2(vals[8 * g + 6] * mul, vals[8 * g + 7] * mul);
+    sts128(stage + lane * ORB + ((g ^ (lane & (CH - 1))) << 4), u);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < CH; ++it) {
+    const int rr = it * ROWS_PER_IT + lane / CH;
+    const int g = lane % CH;
+    if (rr < rows_valid) {
+      const uint4 u = lds128(stage + rr * ORB + ((g ^ (rr & (CH - 1))) << 4));
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbase) + ((long long)(row_first + rr) * ld) * 2 + g * 16) = u;
+    }
+  }
+  __syncwarp();
+}
+
+
 }  // namespace vj

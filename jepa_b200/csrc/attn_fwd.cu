@@ -18,6 +18,8 @@
 //               The running max is only refreshed (and O / l rescaled in TMEM) when it grew by more
 //               than 2^8 ("lazy rescale"), so the O accumulator normally never leaves TMEM until the
 //               final 1/l normalisation.
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "vjepa_b200.h"
 
@@ -338,6 +340,21 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   return 0;
 }
 
+// second-generation kernel (attn_fwd2.cu): persistent, two query tiles per CTA, ping-pong softmax groups
+template <int HD>
+int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
+                     float scale, cudaStream_t s);
+
+// VJ_ATTN_FWD=1 selects the first-generation kernel (one query tile per CTA, two CTAs per SM) - kept for A/B timing
+static int attn_fwd_generation() {
+  static int gen = -1;
+  if (gen < 0) {
+    const char* e = getenv("VJ_ATTN_FWD");
+    gen = (e && e[0] == '1') ? 1 : 2;
+  }
+  return gen;
+}
+
 }  // namespace vj
 
 extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* cu_seqlens, int nseq, int max_len,
@@ -348,6 +365,14 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_fwd: empty problem");
   VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "vj_attn_fwd: pointers must be 16-byte aligned");
+  if (attn_fwd_generation() == 2) {
+    switch (HD) {
+      case 32: return launch_attn_fwd2<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      case 64: return launch_attn_fwd2<64>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      case 128: return launch_attn_fwd2<128>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      default: break;
+    }
+  }
   switch (HD) {
     case 32: return launch_attn_fwd<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
     case 64: return launch_attn_fwd<64>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);

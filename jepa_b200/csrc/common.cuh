@@ -239,6 +239,20 @@ VJ_DEVINL float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, a twentieth of a bf16 ulp), 2^n added straight into the exponent field.  Softmax at head
+// dims 64 / 32 is bound by the 16 exp/clk/SM MUFU pipe; a fraction of the exponentials is moved here (FA4's trick).
+// Valid for x <= ~120; x below -126 is clamped (result ~1e-38, i.e. 0 after the bf16 rounding).
+VJ_DEVINL float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: round(x) sits in the low mantissa bits of t
+  const float f = x - (t - 12582912.0f);
+  float q = fmaf(f, 0.0551716648f, 0.2426111251f);
+  q = fmaf(q, f, 0.6932609677f);
+  q = fmaf(q, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
 // Shared-memory matrix descriptor (tcgen05 "version 1").  Offsets in bytes (16B granules).
 // layout_type: 0 none, 2 128B swizzle, 4 64B swizzle, 6 32B swizzle.
 VJ_DEVINL uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,

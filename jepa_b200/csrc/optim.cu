@@ -214,14 +214,24 @@ namespace vj {
 struct AdamGroups {
   float lr[4], wd[4];
 };
+// STEP_DEV: the step count lives on the device (fp32 scalar, like torch's capturable / fused AdamW): the kernel uses
+// *step_dev + 1 and a one-thread tail kernel advances it ONLY when the step was not skipped by the GradScaler, so the
+// bias correction and the checkpointed `step` stay exact across overflow skips.  shadow (nullable): bf16 copy of the
+// updated parameters, i.e. next step's tensor-core operands, emitted in the same pass (saves the separate cast kernel).
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                          float4* __restrict__ m, float4* __restrict__ v,
                                                          const unsigned char* __restrict__ gid, long long n4,
                                                          AdamGroups hp, float beta1, float beta2, float eps, float bc1,
                                                          float bc2_sqrt, const float* __restrict__ inv_scale,
-                                                         const float* __restrict__ found_inf) {
+                                                         const float* __restrict__ found_inf,
+                                                         const float* __restrict__ step_dev, uint2* __restrict__ shadow) {
   if (found_inf != nullptr && *found_inf != 0.f) return;
   const float gs = inv_scale ? *inv_scale : 1.0f;
+  if (step_dev != nullptr) {
+    const double step = (double)*step_dev + 1.0;       // once per thread, in double like the host path
+    bc1 = float(1.0 - pow((double)beta1, step));
+    bc2_sqrt = float(sqrt(1.0 - pow((double)beta2, step)));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const unsigned id = gid[i >> 4];
     if (id > 3) continue;
@@ -241,27 +251,76 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float4* __restrict__ p,
     VJ_ADAM1(x) VJ_ADAM1(y) VJ_ADAM1(z) VJ_ADAM1(w)
 #undef VJ_ADAM1
     p[i] = pp; m[i] = mm; v[i] = vv;
+    if (shadow != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(pp.x, pp.y);
+      o.y = pack_bf16x2(pp.z, pp.w);
+      shadow[i] = o;
+    }
+  }
+}
+__global__ void step_advance_kernel(float* step_dev, const float* __restrict__ found_inf) {
+  if (found_inf == nullptr || *found_inf == 0.f) *step_dev += 1.0f;
+}
+// k = k*m + (1-m)*q with the bf16 shadow of the new k emitted in the same pass (target-encoder EMA, train.py:484-487)
+__global__ void __launch_bounds__(256) ema_shadow_kernel(float4* __restrict__ k, const float4* __restrict__ q, long long n4,
+                                                         float m, float one_minus_m, uint2* __restrict__ shadow) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = k[i];
+    const float4 b = q[i];
+    // op-for-op like param_k.mul_(m).add_((1.-m)*param_q): two roundings per element, no FMA contraction
+    a.x = __fadd_rn(__fmul_rn(a.x, m), __fmul_rn(one_minus_m, b.x));
+    a.y = __fadd_rn(__fmul_rn(a.y, m), __fmul_rn(one_minus_m, b.y));
+    a.z = __fadd_rn(__fmul_rn(a.z, m), __fmul_rn(one_minus_m, b.z));
+    a.w = __fadd_rn(__fmul_rn(a.w, m), __fmul_rn(one_minus_m, b.w));
+    k[i] = a;
+    uint2 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    shadow[i] = o;
   }
 }
 }  // namespace vj
 
 extern "C" int vj_adamw_flat(float* p, const float* g, float* m, float* v, const unsigned char* group_ids, long long n,
                              const float* lr4, const float* wd4, float beta1, float beta2, float eps, int step,
-                             const float* inv_scale_dev, const float* found_inf_dev, void* stream_) {
+                             const float* inv_scale_dev, const float* found_inf_dev, float* step_dev, void* shadow_bf16,
+                             void* stream_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   VJ_CHECK_ARG(p && g && m && v && group_ids && lr4 && wd4, "vj_adamw_flat: null pointer");
-  VJ_CHECK_ARG(n % 64 == 0 && step >= 1, "vj_adamw_flat: n %% 64 == 0 and step >= 1 required");
+  VJ_CHECK_ARG(n % 64 == 0 && (step >= 1 || step_dev != nullptr), "vj_adamw_flat: n %% 64 == 0 and step >= 1 required");
   VJ_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                  reinterpret_cast<uintptr_t>(v)) & 15) == 0, "vj_adamw_flat: 16-byte alignment required");
+  VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0, "vj_adamw_flat: shadow must be 8-byte aligned");
   if (n <= 0) return 0;
   vj::AdamGroups hp;
   for (int i = 0; i < 4; ++i) { hp.lr[i] = lr4[i]; hp.wd[i] = wd4[i]; }   // host arrays
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int hstep = step >= 1 ? step : 1;
+  const double bc1 = 1.0 - pow((double)beta1, (double)hstep);
+  const double bc2 = 1.0 - pow((double)beta2, (double)hstep);
   vj::adamw_flat_kernel<<<vj::flat_grid(n / 4, 256), 256, 0, s>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), group_ids, n / 4, hp, beta1, beta2, eps, float(bc1), float(sqrt(bc2)),
-      inv_scale_dev, found_inf_dev);
+      inv_scale_dev, found_inf_dev, step_dev, reinterpret_cast<uint2*>(shadow_bf16));
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  if (step_dev != nullptr) {
+    vj::step_advance_kernel<<<1, 1, 0, s>>>(step_dev, found_inf_dev);
+    VJ_CUDA(cudaGetLastError());
+    vj::count_launch(1);
+  }
+  return 0;
+}
+
+extern "C" int vj_ema_update_shadow(float* k, const float* q, long long n, float m, float one_minus_m, void* shadow_bf16,
+                                    void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(k && q && shadow_bf16, "vj_ema_update_shadow: null pointer");
+  VJ_CHECK_ARG(n % 4 == 0 && ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(q)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0, "vj_ema_update_shadow: alignment");
+  if (n <= 0) return 0;
+  vj::ema_shadow_kernel<<<vj::flat_grid(n / 4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(k), reinterpret_cast<const float4*>(q),
+                                                                  n / 4, m, one_minus_m, reinterpret_cast<uint2*>(shadow_bf16));
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
   return 0;

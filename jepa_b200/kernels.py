@@ -220,3 +220,30 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, inv_scale=None, foun
 def sumsq(x, out):
     _chk(x, F32, "x"); _chk(out, F32, "out")
     _lib.call("vj_sumsq", _p(x), x.numel(), _p(out), _s())
+
+
+def ema_update_shadow(k_flat, q_flat, m, shadow):
+    _chk(k_flat, F32, "k"); _chk(q_flat, F32, "q"); _chk(shadow, BF16, "shadow")
+    _lib.call("vj_ema_update_shadow", _p(k_flat), _p(q_flat), k_flat.numel(), float(m), float(1.0 - m), _p(shadow), _s())
+
+
+def grad_unscale_stats(gflat, seg, sumsq_out, inv_scale=None, found_inf=None, write_back=True):
+    """One pass over a flat fp32 gradient buffer: optional in-place unscale, non-finite flag, per-tensor sum of squares."""
+    _chk(gflat, F32, "gflat"); _chk(seg, torch.uint16, "seg"); _chk(sumsq_out, F32, "sumsq_out")
+    _lib.call("vj_grad_unscale_stats", _p(gflat), _p(seg), gflat.numel(), _p(inv_scale), _p(found_inf), _p(sumsq_out),
+              int(bool(write_back)), _s())
+
+
+def seg_abs_sum(x, seg, out):
+    _chk(x, F32, "x"); _chk(seg, torch.uint16, "seg"); _chk(out, F32, "out")
+    _lib.call("vj_seg_abs_sum", _p(x), _p(seg), x.numel(), _p(out), _s())
+
+
+def clip_coef(sumsq, max_norm, total_norm_out, coef_out):
+    _chk(sumsq, F32, "sumsq")
+    _lib.call("vj_clip_coef", _p(sumsq), sumsq.numel(), float(max_norm), _p(total_norm_out), _p(coef_out), _s())
+
+
+def scale_flat(x, coef_dev):
+    _chk(x, F32, "x"); _chk(coef_dev, F32, "coef")
+    _lib.call("vj_scale_flat", _p(x), x.numel(), _p(coef_dev), _s())

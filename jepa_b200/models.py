@@ -208,6 +208,10 @@ class VisionTransformer(nn.Module):
         self._scratch = {}
         self._spec = engine.StackSpec(embed_dim, num_heads, int(embed_dim * mlp_ratio), depth, "blocks")
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._store.invalidate_shadow()      # parameters changed behind the optimizer's back: re-cast the bf16 operands
+
     def __deepcopy__(self, memo):
         import copy
         cls = self.__class__
@@ -397,6 +401,7 @@ class VisionTransformerPredictor(nn.Module):
                                       "predictor_blocks")
 
     __deepcopy__ = VisionTransformer.__deepcopy__
+    _load_from_state_dict = VisionTransformer._load_from_state_dict
 
     def _init_pos_embed(self, pos_embed):
         embed_dim = pos_embed.size(-1)

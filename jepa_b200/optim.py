@@ -19,6 +19,23 @@ from . import _lib
 from . import kernels as K
 
 
+class FlatGradScaler(torch.cuda.amp.GradScaler):
+    """torch's GradScaler (same state_dict, same scale / growth policy, app/vjepa/utils.py:209) whose unscale pass over
+    FlatAdamW-owned flat gradient buffers is one of our kernels instead of torch._amp_foreach_non_finite_check_and_unscale_
+    over hundreds of views; anything not in a flat buffer still goes through torch's implementation."""
+
+    def _unscale_grads_(self, optimizer, inv_scale, found_inf, allow_fp16):
+        if not isinstance(optimizer, FlatAdamW):
+            return super()._unscale_grads_(optimizer, inv_scale, found_inf, allow_fp16)
+        inv = inv_scale.reshape(1).contiguous()
+        fi = found_inf.reshape(1)
+        rest = optimizer.unscale_flat_(inv, fi)
+        if rest:
+            grads = [p.grad for p in rest]
+            torch._amp_foreach_non_finite_check_and_unscale_(grads, found_inf, inv_scale)
+        return {found_inf.device: found_inf}
+
+
 class FlatAdamW(torch.optim.Optimizer):
     _step_supports_amp_scaling = True
 
@@ -57,11 +74,13 @@ class FlatAdamW(torch.optim.Optimizer):
             gid[off // 64:(off + n + 63) // 64] = gi if p.requires_grad else 255   # frozen (pos_embed): untouched
         m = torch.zeros(store.total, dtype=torch.float32, device=dev)
         v = torch.zeros(store.total, dtype=torch.float32, device=dev)
-        step = torch.zeros((), dtype=torch.float32)
+        # the step count is a DEVICE scalar (as in torch's fused / capturable AdamW): the kernel advances it only when the
+        # GradScaler did not skip the step, so bias correction and the checkpointed `step` do not drift on overflow skips
+        step = torch.zeros((), dtype=torch.float32, device=dev)
         for _, p in members:       # resume: carry per-tensor state (e.g. from load_state_dict) into the flat buffers
             old = self.state.get(p, {})
             if "step" in old:
-                step = torch.as_tensor(float(old["step"]), dtype=torch.float32)
+                step.fill_(float(old["step"]))
                 break
         for gi, p in members:
             off, n, shape = store.offsets[p._vj_name]
@@ -94,6 +113,36 @@ class FlatAdamW(torch.optim.Optimizer):
                 return None
         return base
 
+    # ------------------------------------------------------------------------------------------ GradScaler hook
+    @torch.no_grad()
+    def unscale_flat_(self, inv_scale, found_inf):
+        """scaler.unscale_ for gradients that live in flat buffers: ONE kernel per backbone unscales in place, raises the
+        non-finite flag and leaves per-tensor sums of squares behind for grad_logger / clip_grad_norm_ (no host sync).
+        Returns the parameters it did not cover (torch's foreach path handles those)."""
+        by_store, leftovers = self._flat_plan()
+        self._grad_stats = {}
+        for store, members in by_store.values():
+            base = self._flat_grad_base(store, members)
+            if base is None:
+                leftovers.extend(members)
+                continue
+            seg, names = store.segments()
+            sumsq = torch.zeros(len(names), dtype=torch.float32, device=store.flat.device)
+            _lib.call("vj_grad_unscale_stats", base, seg.data_ptr(), store.total, K._p(inv_scale), K._p(found_inf),
+                      sumsq.data_ptr(), 1, K._s())
+            self._grad_stats[id(store)] = (store, base, sumsq, names)
+            store._grad_sumsq = (base, getattr(store, "_grad_gen", 0), sumsq)   # reused by grad_logger / clip_grad_norm_
+        return [p for _, p in leftovers if p.grad is not None]
+
+    def grad_stats_for(self, store):
+        """(sumsq tensor, names) left by the last unscale_flat_ for this store, or None."""
+        hit = getattr(self, "_grad_stats", {}).get(id(store))
+        return None if hit is None else (hit[2], hit[3])
+
+    def zero_grad(self, set_to_none=True):
+        self._grad_stats = {}
+        return super().zero_grad(set_to_none=set_to_none)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -116,14 +165,15 @@ class FlatAdamW(torch.optim.Optimizer):
                 leftovers.extend(members)
                 continue
             st = self._flat_state(store, members)
-            st["step"] += 1
             lr4 = (ctypes.c_float * 4)(*[float(g['lr']) for g in self.param_groups[:4]] + [0.0] * (4 - min(4, len(self.param_groups))))
             wd4 = (ctypes.c_float * 4)(*[float(g['weight_decay']) for g in self.param_groups[:4]] + [0.0] * (4 - min(4, len(self.param_groups))))
             beta1, beta2 = self.param_groups[0]['betas']
             _lib.call("vj_adamw_flat", store.flat.data_ptr(), base, st["m"].data_ptr(), st["v"].data_ptr(),
                       st["gid"].data_ptr(), store.total, ctypes.cast(lr4, ctypes.c_void_p), ctypes.cast(wd4, ctypes.c_void_p),
-                      float(beta1), float(beta2), float(self.param_groups[0]['eps']), int(st["step"]),
-                      K._p(inv_scale), K._p(found_inf), K._s())
+                      float(beta1), float(beta2), float(self.param_groups[0]['eps']), 0,
+                      K._p(inv_scale), K._p(found_inf), st["step"].data_ptr(), store.shadow.data_ptr(), K._s())
+            store.mark_shadow_fresh()     # the kernel wrote next step's bf16 operands with the update (if not skipped,
+                                          # and if skipped the previous shadow is still the right one)
 
         for gi, p in leftovers:
             if p.grad is None:

@@ -35,6 +35,8 @@ class FlatParamStore:
         self.offsets = {}     # name -> (offset, numel, shape)
         self.total = 0
         self._params = None
+        self._shadow_fresh = False   # set by the kernels that emit the bf16 shadow together with a parameter update
+        self._seg = None             # uint16 per 64-element block -> index into named parameters (0xFFFF: frozen / padding)
 
     def __deepcopy__(self, memo):
         return FlatParamStore()  # copies re-adopt their own (deep-copied) parameters lazily
@@ -75,6 +77,8 @@ class FlatParamStore:
                 p._vj_store, p._vj_name = self, n
         self.flat, self.offsets, self.total, self._params = flat, offsets, off, named
         self.shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
+        self._shadow_fresh = False
+        self._seg = None
         return self
 
     def owns(self, p):
@@ -87,7 +91,33 @@ class FlatParamStore:
 
     # -- per-step products ---------------------------------------------------------------------
     def refresh_shadow(self):
+        """bf16 operands of this forward.  The fused AdamW / EMA kernels already wrote them together with the parameter
+        update (one pass instead of update + cast); that copy is valid for exactly one refresh, anything else that may
+        have touched the parameters in between (load_state_dict, manual edits) is covered by casting again."""
+        if self._shadow_fresh:
+            self._shadow_fresh = False
+            return
         K.cast_f32_bf16(self.flat, self.shadow)
+
+    def mark_shadow_fresh(self):
+        self._shadow_fresh = True
+
+    def invalidate_shadow(self):
+        self._shadow_fresh = False
+
+    def segments(self):
+        """(seg uint16 [total/64] on the device, names): block -> index of the TRAINABLE tensor it belongs to."""
+        if self._seg is None:
+            seg = torch.full((self.total // ALIGN,), 0xFFFF, dtype=torch.int32)
+            names = []
+            for n, p in self._params:
+                if not p.requires_grad:
+                    continue
+                off, cnt, _ = self.offsets[n]
+                seg[off // ALIGN:(off + cnt + ALIGN - 1) // ALIGN] = len(names)
+                names.append(n)
+            self._seg = (seg.to(torch.uint16).to(self.flat.device), names)
+        return self._seg
 
     def bf16(self, name):
         o, n, shape = self.offsets[name]
@@ -98,6 +128,7 @@ class FlatParamStore:
         return self.flat[o:o + n].view(shape)
 
     def new_grad_buffer(self):
+        self._grad_gen = getattr(self, "_grad_gen", 0) + 1     # invalidates cached per-tensor gradient statistics
         return torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
 
     def grad_view(self, gflat, name):

@@ -109,4 +109,32 @@ def ema_update(encoder, target_encoder, m):
     qs, ks = q._store.adopt(q), k._store.adopt(k)
     if qs.offsets != ks.offsets:
         raise RuntimeError("encoder / target_encoder parameter layouts differ")
-    K.ema_update(ks.flat, qs.flat, m)
+    # the bf16 tensor-core operands of the target's next forward leave in the same pass (no separate cast launch)
+    K.ema_update_shadow(ks.flat, qs.flat, m, ks.shadow)
+    ks.mark_shadow_fresh()
+
+
+@torch.no_grad()
+def clip_grad_norm_(module, max_norm):
+    """torch.nn.utils.clip_grad_norm_(module.parameters(), max_norm) (L2; app/vjepa/train.py:468-471) for a network whose
+    gradients live in one flat buffer: per-tensor sums of squares (reused from the unscale pass of this step when
+    current) -> total norm and clip coefficient ON THE DEVICE -> one scaling pass that exits immediately when no
+    clipping is needed.  Returns the total norm as a device scalar (float() it like the reference does)."""
+    from .logging_utils import _flat_grad_sumsq
+    bb = unwrap(module)
+    named = [(n, p) for n, p in bb.named_parameters() if p.grad is not None]
+    if not named:
+        return torch.zeros((), device=next(bb.parameters()).device)
+    flat = _flat_grad_sumsq(named)
+    if flat is None or len(flat) != len(named):
+        return torch.nn.utils.clip_grad_norm_([p for _, p in named], max_norm)
+    sumsq = next(iter(flat.values()))[0]
+    store = bb._store
+    out = torch.empty(2, dtype=torch.float32, device=sumsq.device)
+    K.clip_coef(sumsq, max_norm, out[0:1], out[1:2])
+    p0 = named[0][1]
+    base_off = store.offsets[p0._vj_name][0]
+    gflat = torch.as_strided(p0.grad, (store.total,), (1,), storage_offset=p0.grad.storage_offset() - base_off)
+    K.scale_flat(gflat, out[1:2])
+    store._grad_sumsq = None          # the cached statistics describe the unclipped gradients
+    return out[0]

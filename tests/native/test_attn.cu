@@ -195,6 +195,38 @@ int main(int argc, char** argv) {
     perf(16, 32, 32, 1184, true);
     return 0;
   }
+  if (argc > 1 && !strcmp(argv[1], "fwdbig")) {   // forward only: BASELINE sequence lengths, tails, persistence (> 148 work items)
+    fails += run(2, 64, 64, {128}, false);
+    fails += run(2, 64, 64, {1}, false);
+    fails += run(2, 64, 64, {129, 127, 256, 257, 17}, false);
+    fails += run(2, 64, 64, {1568}, false);
+    fails += run(2, 32, 24, {1184, 1192}, false);
+    fails += run(2, 64, 64, {360, 48, 360}, false);
+    fails += run(1, 128, 80, {1568, 200}, false);
+    fails += run(16, 64, 64, {300, 300, 300, 300, 300, 300, 300, 300, 40, 513}, false);   // 480 items: persistent CTAs, mixed 1- / 2-tile items
+    fails += run(16, 32, 24, {520, 300, 300, 300, 300, 300, 300, 300}, false);
+    fails += run(8, 128, 128, {300, 300, 300, 300, 300, 300, 300, 300, 300, 300, 300, 700}, false);
+    perf(16, 64, 32, 1568, false);
+    perf(16, 32, 32, 1184, false);
+    perf(16, 64, 32, 360, false);
+    perf(16, 128, 24, 1568, false);
+    printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL PASSED", fails);
+    return fails ? 1 : 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "bwdbig")) {   // backward at BASELINE predictor lengths, tails, persistence
+    fails += run(2, 32, 24, {128}, true);
+    fails += run(2, 32, 24, {1}, true);
+    fails += run(2, 32, 24, {129, 127, 256, 257, 17, 300}, true);
+    fails += run(2, 32, 24, {1184, 1192}, true);
+    fails += run(1, 32, 32, {3680}, true);
+    fails += run(16, 32, 24, {520, 300, 300, 300, 300, 300, 300, 300}, true);   // 384 items: persistent, mixed 1- / 2-tile items
+    fails += run(2, 64, 64, {360, 48}, true);
+    perf(16, 32, 32, 1184, true);
+    perf(16, 32, 32, 1192, true);
+    perf(16, 64, 32, 360, true);
+    printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL PASSED", fails);
+    return fails ? 1 : 0;
+  }
   fails += run(2, 64, 64, {128}, bwd);
   fails += run(2, 64, 64, {200, 48, 136}, bwd);
   fails += run(3, 32, 24, {296, 40}, bwd);

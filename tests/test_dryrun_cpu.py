@@ -107,7 +107,7 @@ def test_full_step_orchestration_dry_run(dry, monkeypatch):
     # every kernel family was reached
     for k in ("vj_gemm", "vj_attn_fwd", "vj_attn_bwd", "vj_layernorm_fwd", "vj_layernorm_bwd", "vj_im2col_tubelets",
               "vj_target_ln_gather", "vj_pred_assemble_fwd", "vj_pred_assemble_bwd", "vj_seq_slice", "vj_l1_loss_fwd",
-              "vj_l1_loss_bwd", "vj_colsum", "vj_cast_f32_bf16", "vj_ema_update", "vj_adamw_step", "vj_token_std_accum"):
+              "vj_l1_loss_bwd", "vj_colsum", "vj_cast_f32_bf16", "vj_ema_update_shadow", "vj_adamw_step", "vj_token_std_accum"):
         assert k in dry, k
     # flat store survived deepcopy / re-adoption: parameters alias their store, target has its own buffer
     eb, tb = enc.backbone, tgt.backbone

@@ -536,10 +536,100 @@ def test_flat_adamw_single_launch_matches_torch(dev):
                     ref_params[p].grad = view.clone()
         before = _lib.load().vj_launch_count()
         opt.step()
-        assert _lib.load().vj_launch_count() - before == 2      # one launch per backbone
+        assert _lib.load().vj_launch_count() - before == 4      # per backbone: one AdamW launch + the 1-thread step-counter advance
         ref.step()
     for p, c in ref_params.items():
         assert rel_l2(p.detach().cpu(), c.detach().cpu()) < 2e-6
     assert torch.equal(enc.backbone.pos_embed.detach(), pos0)
     sd = opt.state_dict()
     assert len(sd["state"]) == len(ref_params) and float(next(iter(sd["state"].values()))["step"]) == 3.0
+
+
+def test_flat_grad_statistics_scaler_clip_and_loggers(dev):
+    """f1 / f2: the segmented single-pass kernels behind scaler.unscale_, grad_logger, adamw_logger and
+    clip_grad_norm_ against the reference's own formulas (src/utils/logging.py:91-118, app/vjepa/train.py:462-471) and
+    torch's implementations, on a ViT-Tiny encoder + predictor with synthetic flat gradients."""
+    from app.vjepa.utils import init_opt, init_video_model
+    from jepa_b200 import step as vj
+    from jepa_b200.optim import FlatGradScaler
+    from src.utils.logging import adamw_logger, grad_logger
+    torch.manual_seed(3)
+    enc, pred = init_video_model(device=dev, patch_size=16, num_frames=8, tubelet_size=2, model_name="vit_tiny",
+                                 crop_size=224, pred_depth=2, pred_embed_dim=384, uniform_power=True,
+                                 use_mask_tokens=True, num_mask_tokens=2, use_sdpa=True)
+    for net in (enc, pred):
+        net.backbone._store.adopt(net.backbone)
+    opt, scaler, sch, wds = init_opt(enc, pred, iterations_per_epoch=10, start_lr=1e-3, ref_lr=2e-3, warmup=1, num_epochs=2,
+                                     wd=0.04, final_wd=0.4, mixed_precision=True)
+    assert isinstance(scaler, FlatGradScaler)
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def fake_backward(scale, poison=False):
+        for net in (enc, pred):
+            st = net.backbone._store
+            gflat = st.new_grad_buffer()
+            for n, p in net.backbone.named_parameters():
+                if p.requires_grad:
+                    view = st.grad_view(gflat, n)
+                    view.copy_(torch.randn(view.shape, device=dev, generator=gen) * 0.01 * scale)
+                    p.grad = view
+        if poison:
+            enc.backbone.blocks[3].mlp.fc1.weight.grad[5, 7] = float("inf")
+
+    # ---- unscale + per-tensor norms + loggers
+    sch.step(); wds.step()
+    fake_backward(65536.0)
+    ref_norm = {n: float(p.grad.double().norm() / 65536.0) for n, p in enc.named_parameters() if p.grad is not None}
+    scaler._lazy_init_scale_growth_tracker(dev)
+    scaler.unscale_(opt)
+    for n, p in enc.named_parameters():
+        if p.grad is not None:
+            assert abs(float(p.grad.double().norm()) - ref_norm[n]) <= 1e-5 * ref_norm[n] + 1e-12, n
+    gs = grad_logger(enc.named_parameters())
+    w = [v for n, v in ref_norm.items() if not (n.endswith(".bias") or enc.get_parameter(n).dim() == 1)]
+    assert abs(gs.avg - sum(w) / len(w)) < 1e-5 * gs.avg and abs(gs.max - max(w)) < 1e-5 * gs.max and abs(gs.min - min(w)) < 1e-5 * gs.max
+    qkv = [v for n, v in ref_norm.items() if "qkv" in n and n.endswith("weight")]
+    assert abs(gs.first_layer - qkv[0]) < 1e-5 * qkv[0] and abs(gs.last_layer - qkv[-1]) < 1e-5 * qkv[-1]
+    # ---- clip_grad_norm_ on the device == torch's
+    ref_grads = [p.grad.clone() for p in pred.parameters() if p.grad is not None]
+    total_ref = torch.nn.utils.clip_grad_norm_([torch.nn.Parameter(g.clone()) for g in ref_grads], 1e9)   # norm only
+    refp = [torch.nn.Parameter(torch.zeros_like(g)) for g in ref_grads]
+    for q, g in zip(refp, ref_grads):
+        q.grad = g.clone()
+    max_norm = float(total_ref) * 0.5
+    torch.nn.utils.clip_grad_norm_(refp, max_norm)
+    total = vj.clip_grad_norm_(pred, max_norm)
+    assert abs(float(total) - float(total_ref)) < 1e-5 * float(total_ref)
+    for q, p in zip(refp, [p for p in pred.parameters() if p.grad is not None]):
+        assert rel_l2(p.grad.cpu(), q.grad.cpu()) < 1e-6
+    before = [p.grad.clone() for p in enc.parameters() if p.grad is not None]
+    vj.clip_grad_norm_(enc, 1e9)                              # no clipping needed: gradients untouched
+    assert all(torch.equal(a, p.grad) for a, p in zip(before, [p for p in enc.parameters() if p.grad is not None]))
+    # ---- optimizer step: device-side step counter, bf16 shadow emitted with the update
+    scaler.step(opt); scaler.update()
+    st0 = opt.state[enc.backbone.blocks[0].attn.qkv.weight]
+    assert st0["step"].is_cuda and float(st0["step"]) == 1.0
+    store = enc.backbone._store
+    assert store._shadow_fresh and torch.equal(store.shadow, store.flat.to(torch.bfloat16))
+    am = adamw_logger(opt)
+    ref1 = [float(s["exp_avg"].abs().mean()) for s in opt.state_dict()["state"].values()]
+    ref2 = [float(s["exp_avg_sq"].abs().mean()) for s in opt.state_dict()["state"].values()]
+    assert abs(am["exp_avg"].avg - sum(ref1) / len(ref1)) < 1e-5 * am["exp_avg"].avg
+    assert abs(am["exp_avg_sq"].max - max(ref2)) < 1e-5 * am["exp_avg_sq"].max and am["exp_avg"].count == len(ref1)
+    opt.zero_grad()
+    # ---- an overflowing step is skipped: parameters, moments AND the step count stay put; the scale backs off
+    p_before = store.flat.clone()
+    sch.step(); wds.step()
+    fake_backward(65536.0, poison=True)
+    scaler.unscale_(opt)
+    scaler.step(opt); scaler.update()
+    assert torch.equal(store.flat, p_before) and float(st0["step"]) == 1.0 and float(scaler.get_scale()) == 32768.0
+    opt.zero_grad()
+    # ---- EMA emits the target's bf16 operands in the same pass, bit-exact with the reference op sequence
+    import copy
+    tgt = copy.deepcopy(enc)
+    k0 = tgt.backbone._store.adopt(tgt.backbone).flat.clone()
+    vj.ema_update(enc, tgt, 0.998)
+    ref = k0.clone(); ref.mul_(0.998).add_((1. - 0.998) * store.flat)
+    ks = tgt.backbone._store
+    assert torch.equal(ks.flat, ref) and ks._shadow_fresh and torch.equal(ks.shadow, ref.to(torch.bfloat16))
