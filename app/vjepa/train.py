@@ -27,6 +27,7 @@ from src.utils.distributed import DistributedDataParallel   # flat-buffer gradie
 from app.vjepa.transforms import make_transforms
 from app.vjepa.utils import init_opt, init_video_model, load_checkpoint
 from jepa_b200 import step as vj
+from jepa_b200.checkpoint import AsyncCheckpointer
 from src.datasets.data_manager import init_data
 from src.masks.multiblock3d import MaskCollator as MB3DMaskCollator
 from src.masks.random_tube import MaskCollator as TubeMaskCollator
@@ -210,6 +211,8 @@ def main(args, resume_preempt=False):
             next(momentum_scheduler)
             mask_collator.step()
 
+    checkpointer = AsyncCheckpointer()
+
     def save_checkpoint(epoch, path):
         if rank != 0:
             return
@@ -218,10 +221,11 @@ def main(args, resume_preempt=False):
             'scaler': None if scaler is None else scaler.state_dict(), 'target_encoder': target_encoder.state_dict(),
             'epoch': epoch, 'loss': loss_meter.avg, 'batch_size': batch_size, 'world_size': world_size, 'lr': lr,
         }
-        try:
-            torch.save(save_dict, path)
-        except Exception as e:
-            logger.info(f'Encountered exception when saving checkpoint: {e}')
+        # asynchronous: device->host snapshot enqueued now, serialisation + disk write in a background thread
+        checkpointer.save(save_dict, path)
+        if checkpointer.error is not None:
+            logger.info(f'Encountered exception when saving checkpoint: {checkpointer.error}')
+            checkpointer.error = None
 
     logger.info('Initializing loader...')
     loader = iter(unsupervised_loader)
@@ -346,3 +350,6 @@ def main(args, resume_preempt=False):
             save_checkpoint(epoch + 1, latest_path)
             if save_every_freq > 0 and epoch % save_every_freq == 0:
                 save_checkpoint(epoch + 1, os.path.join(folder, f'{tag}-e{epoch}.pth.tar'))
+    checkpointer.wait()
+    if checkpointer.error is not None:
+        logger.info(f'Encountered exception when saving checkpoint: {checkpointer.error}')

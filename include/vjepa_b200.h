@@ -41,7 +41,8 @@ long long vj_launch_count(void);
  * a_mn = 0: A stored [M,K] (K contiguous, ld = lda);  a_mn = 1: A stored [K,M] (M contiguous).
  * b_mn = 0: B stored [N,K];                            b_mn = 1: B stored [K,N].
  * Supported (a_mn,b_mn): (0,0) forward / nn.Linear, (0,1) dgrad, (1,1) wgrad.
- * d_f32: D is fp32 (else bf16).  accumulate!=0 or split_k>1 reduce-add into fp32 D.
+ * d_f32: D is fp32 (else bf16).  accumulate!=0 or split_k>1 reduce-add into fp32 D.  split_k < 0 (with accumulate,
+ * no epilogue): stream-K - the (tile, k-block) space is cut into one equal contiguous range per SM (weight gradients).
  * bias: fp32 [N] or NULL.  aux: bf16 or fp32 (aux_f32) tile source for ADD / MUL / DGELU.  An fp32 aux may be
  * row-mapped: row r reads aux row aux_rowmap[r] if given, else r % aux_period if aux_period > 0, else r (pos-embed
  * add of the patch-embed GEMM); a bf16 aux is a plain [M,N] matrix (residual stream / saved gelu') and does not

@@ -50,8 +50,9 @@ struct Bwd2Cfg {
   static constexpr int QDO_OFF = KV_OFF + 8 * TILE;           // [2 stages][Q, dO]
   static constexpr int DS_OFF = QDO_OFF + 4 * TILE;           // [2 key tiles] dS^T tiles, 32 KB each
   static constexpr int STAT_OFF = DS_OFF + 2 * A::P_BYTES;    // [2 slots][lse 128 | delta 128] floats
-  static constexpr int DQS_OFF = STAT_OFF + 2048;             // 4 warps x [32 rows x 32 fp32] dQ staging
-  static constexpr int BAR_OFF = DQS_OFF + 4 * 4096;
+  static constexpr int DQS_OFF = STAT_OFF + 2048;             // [2 groups][4 warps] x [32 rows x 32 fp32] dQ staging (each
+                                                              // warp only waits for ITS OWN earlier TMA reduce-add)
+  static constexpr int BAR_OFF = DQS_OFF + 8 * 4096;
   static constexpr int NBARS = 34;
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
   static_assert(SMEM_BYTES <= 232448, "attn_bwd2 shared memory budget exceeded");
@@ -297,7 +298,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
     const uint32_t stats = smem_u32(smem + B::STAT_OFF);
     const uint32_t ps = sDS + g * C::P_BYTES;
-    const uint32_t dqs = smem_u32(smem + B::DQS_OFF) + qd * 4096;
+    const uint32_t dqs = smem_u32(smem + B::DQS_OFF) + (g * 4 + qd) * 4096;
     const uint32_t tST = tmem_base + (g ? B::TM_ST1 : B::TM_ST0) + lane_addr;
     const int col0 = half * 64;
     const int my_bar = 2 + g, other_bar = 3 - g;

@@ -33,6 +33,8 @@ constexpr int kEpiBufBytes = 4096;
 struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n, split_k, kb_total, kb_per_split;
+  int stream_k;             // 1: every CTA takes one contiguous range of `sk_chunk` k-blocks of the linearised (tile, k-block)
+  long long sk_chunk;       //    space (perfect balance, no wave quantisation); partial tiles reduce-add like split-K ones
   const float* bias;
   int epi;
   const void* aux;
@@ -70,6 +72,42 @@ struct GemmCfg {
 VJ_DEVINL uint32_t swz_off(int row, int chunk, bool rows128) {
   return rows128 ? uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4))
                  : uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+// Work decomposition shared by the three warp roles.  Classic: work item w = blockIdx.x, blockIdx.x + gridDim.x, ...
+// over tiles x split_k.  Stream-K: the CTA walks its contiguous k-block range, one (tile, k-range) piece at a time.
+struct WorkCursor {
+  long long cur, end;
+};
+VJ_DEVINL WorkCursor work_begin(const GemmParams& p) {
+  WorkCursor c;
+  if (p.stream_k) {
+    const long long total_kb = (long long)p.tiles_m * p.tiles_n * p.kb_total;
+    c.cur = (long long)blockIdx.x * p.sk_chunk;
+    c.end = min(total_kb, c.cur + p.sk_chunk);
+  } else {
+    c.cur = blockIdx.x;
+    c.end = (long long)p.tiles_m * p.tiles_n * p.split_k;
+  }
+  return c;
+}
+VJ_DEVINL bool work_next(const GemmParams& p, WorkCursor& c, int& t, int& kb0, int& kb1) {
+  if (c.cur >= c.end) return false;
+  if (p.stream_k) {
+    t = int(c.cur / p.kb_total);
+    kb0 = int(c.cur - (long long)t * p.kb_total);
+    const long long take = min((long long)(p.kb_total - kb0), c.end - c.cur);
+    kb1 = kb0 + int(take);
+    c.cur += take;
+  } else {
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int split = int(c.cur / tiles);
+    t = int(c.cur - (long long)split * tiles);
+    kb0 = split * p.kb_per_split;
+    kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+    c.cur += gridDim.x;
+  }
+  return true;
 }
 
 VJ_DEVINL void named_bar_sync(int id, int nthreads) {
@@ -194,13 +232,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int split = w / tiles;
-        const int t = w - split * tiles;
+      WorkCursor wc = work_begin(p);
+      int t, kb0, kb1;
+      while (work_next(p, wc, t, kb0, kb1)) {
         const int m0 = (t / p.tiles_n) * BM;
         const int n0 = (t % p.tiles_n) * BN;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -236,10 +272,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int split = w / tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      WorkCursor wc = work_begin(p);
+      int t, kb0, kb1;
+      while (work_next(p, wc, t, kb0, kb1)) {
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * BN;
@@ -306,15 +341,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int i = 0; i < kAuxRing; ++i) ring_issue(i);
     }
 
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int split = w / tiles;
-      const int t = w - split * tiles;
+    WorkCursor wc = work_begin(p);
+    int t, kb0, kb1;
+    while (work_next(p, wc, t, kb0, kb1)) {
       const int m0 = (t / p.tiles_n) * BM;
       const int n0 = (t % p.tiles_n) * BN;
 
       named_bar_sync(1, kEpiWarps * 32);
-      for (int i = etid; i < BN; i += kEpiWarps * 32)
-        sts32f(bias_u32 + 4 * i, (p.bias != nullptr && split == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f);
+      for (int i = etid; i < BN; i += kEpiWarps * 32)   // the bias joins the piece that holds the first k-block of its tile
+        sts32f(bias_u32 + 4 * i, (p.bias != nullptr && kb0 == 0 && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f);
       named_bar_sync(1, kEpiWarps * 32);
 
       const int row0 = m0 + q * 32;
@@ -514,7 +549,11 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     configured = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
-  const int grid = total < num_sms() ? total : num_sms();
+  int grid = total < num_sms() ? total : num_sms();
+  if (p.stream_k) {
+    const long long total_kb = (long long)p.tiles_m * p.tiles_n * p.kb_total;
+    grid = int((total_kb + p.sk_chunk - 1) / p.sk_chunk);
+  }
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tD, tX, p);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
@@ -573,7 +612,8 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
                    (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                "vj_gemm: operands must be 16-byte aligned");
   VJ_CHECK_ARG(epi >= VJ_EPI_NONE && epi <= VJ_EPI_GELU_GRAD, "vj_gemm: bad epilogue %d", epi);
-  VJ_CHECK_ARG(!(accumulate || split_k > 1) || d_f32, "vj_gemm: accumulate/split-K needs fp32 D");
+  VJ_CHECK_ARG(!(accumulate || split_k > 1 || split_k < 0) || d_f32, "vj_gemm: accumulate/split-K needs fp32 D");
+  VJ_CHECK_ARG(split_k >= 0 || (epi == VJ_EPI_NONE && accumulate), "vj_gemm: stream-K (split_k < 0) is for accumulating fp32 GEMMs");
   if (epi == VJ_EPI_ADD || epi == VJ_EPI_DGELU || epi == VJ_EPI_MUL) {
     VJ_CHECK_ARG(aux != nullptr, "vj_gemm: epilogue %d needs aux", epi);
     VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(aux) & 15) == 0 && ldaux % (aux_f32 ? 4 : 8) == 0,
@@ -587,6 +627,17 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = N / BN;
   p.kb_total = (K + BK - 1) / BK;
+  // split_k < 0: stream-K - the linearised (tile, k-block) space is cut into one equal contiguous range per SM, so no SM
+  // idles in a ragged last wave (the weight-gradient GEMMs have 32..128 output tiles for 148 SMs); every piece reduce-adds
+  p.stream_k = 0;
+  p.sk_chunk = 0;
+  if (split_k < 0) {
+    const long long total_kb = (long long)p.tiles_m * p.tiles_n * p.kb_total;
+    const long long ctas = total_kb < num_sms() ? total_kb : num_sms();
+    p.stream_k = 1;
+    p.sk_chunk = (total_kb + ctas - 1) / ctas;
+    split_k = 1;
+  }
   if (split_k < 1) split_k = 1;
   if (split_k > p.kb_total) split_k = p.kb_total;
   p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
@@ -595,7 +646,7 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.epi = epi;
   p.aux = aux; p.ldaux = ldaux; p.aux_f32 = aux_f32; p.aux_rowmap = aux_rowmap; p.aux_period = aux_period;
   p.has_auxout = ((epi == VJ_EPI_GELU || epi == VJ_EPI_GELU_GRAD) && aux_out != nullptr) ? 1 : 0;
-  p.reduce_add = (accumulate || p.split_k > 1) ? 1 : 0;
+  p.reduce_add = (accumulate || p.split_k > 1 || p.stream_k) ? 1 : 0;
   p.alpha = alpha;
   p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;
 

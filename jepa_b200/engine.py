@@ -107,10 +107,11 @@ class BlockSaved:
     __slots__ = ("x_in", "mean1", "rstd1", "ln1", "qkv", "attn", "lse", "x_mid", "mean2", "rstd2", "ln2", "h", "g")
 
 
-def blocks_forward(spec, weights, x, seq, save):
+def blocks_forward(spec, weights, x, seq, save, tap=None):
     """Run the Block stack over token matrix x [T, dim] (bf16).  Returns (x_out, saved list or None).
 
     Block.forward (modules.py:114-120): x = x + proj(attn(LN1(x))); x = x + fc2(gelu(fc1(LN2(x)))).
+    tap(i, x): called with the residual stream after block i (multi-layer feature taps, vision_transformer.py:186-187).
     """
     cu, nseq, max_len, T = seq
     dev = x.device
@@ -147,13 +148,18 @@ def blocks_forward(spec, weights, x, seq, save):
             s.ln1, s.qkv, s.attn, s.lse, s.x_mid, s.ln2, s.h, s.g = ln, qkv, attn, lse, x_mid, ln2, h, g
             saved.append(s)
         x = x_out
+        if tap is not None:
+            tap(len(saved) - 1 if save else tap.count, x)
+            tap.count += 1
     return x, saved
 
 
 def _wgrad(dy, act, grad_out, bias_grad, tokens):
     """grad_out[N_out, K_in] += dy^T act ; bias_grad[N_out] += colsum(dy)."""
     n_out, k_in = grad_out.shape
-    K.gemm(dy, act, grad_out, a_mn=True, b_mn=True, accumulate=True, split_k=_split_k_for(n_out, k_in, tokens))
+    # stream-K (split_k = -1): 32..128 output tiles for 148 SMs - every SM gets the same number of k-blocks instead of a
+    # ragged second wave; all pieces reduce-add into the flat fp32 gradient buffer anyway
+    K.gemm(dy, act, grad_out, a_mn=True, b_mn=True, accumulate=True, split_k=-1)
     if bias_grad is not None:
         K.colsum(dy, bias_grad)
 
@@ -226,7 +232,20 @@ class EncoderSaved:
     pass
 
 
-def encoder_forward(mod, clips, masks, save, final_norm=True):
+class _LayerTaps:
+    """Collects norm(x) after the requested blocks (out_layers, vision_transformer.py:183-190)."""
+
+    def __init__(self, layers, store):
+        self.layers, self.store, self.count, self.outs = set(int(i) for i in layers), store, 0, []
+
+    def __call__(self, i, x):
+        if i in self.layers:
+            y = torch.empty_like(x)
+            K.layernorm_fwd(x, y, self.store.f32("norm.weight"), self.store.f32("norm.bias"), LN_EPS, None, None)
+            self.outs.append(y)
+
+
+def encoder_forward(mod, clips, masks, save, final_norm=True, out_layers=None):
     """VisionTransformer.forward (vision_transformer.py:159-195) for all masks at once.
 
     clips fp32 [B,3,T,H,W]; masks: None or list of int64 [B,K_i].  Returns (out, saved) where out is
@@ -268,6 +287,12 @@ def encoder_forward(mod, clips, masks, save, final_norm=True):
     pos = store.f32("pos_embed").view(N, D)
     K.gemm(patches, w_pe, x, bias=store.f32("patch_embed.proj.bias"), epi=K.EPI_ADD, aux=pos, aux_rowmap=rowmap,
            aux_period=period)
+    if out_layers is not None:      # frozen-encoder feature taps (evals): list of normalised per-layer outputs
+        if save:
+            raise RuntimeError("out_layers is an inference-time feature (frozen encoder); run it under torch.no_grad()")
+        taps = _LayerTaps(out_layers, store)
+        blocks_forward(spec, weights, x, seq, False, tap=taps)
+        return taps.outs, None, segments
     x, bsaved = blocks_forward(spec, weights, x, seq, save)
     out = x
     sv = None

@@ -171,9 +171,7 @@ class VisionTransformer(nn.Module):
         super().__init__()
         self.num_features = self.embed_dim = embed_dim
         self.num_heads = num_heads
-        self.out_layers = out_layers
-        if out_layers is not None:
-            raise NotImplementedError("out_layers (multi-layer feature taps for evals) is outside the pre-training path")
+        self.out_layers = out_layers     # evals: return [norm(x_i) for i in out_layers] (frozen encoder, no grad)
         self.input_size = img_size
         self.patch_size = patch_size
         self.num_frames = num_frames
@@ -272,6 +270,17 @@ class VisionTransformer(nn.Module):
             raise NotImplementedError("bicubic pos-embed interpolation is outside the pre-training path")
         return x.unsqueeze(2)
 
+    @torch.no_grad()
+    def _forward_out_layers(self, x, masks):
+        """vision_transformer.py:183-190 with out_layers set: list of norm(x) after the chosen blocks, each [B, N, D]
+        (or [len(masks)*B, K, D]).  Inference only - the evals use it on the frozen encoder."""
+        xv = self._check_input(x)
+        if masks is not None and len({int(m.shape[1]) for m in masks}) != 1:
+            raise ValueError("out_layers with masks of different sizes cannot be concatenated along batch")
+        outs, _, _ = engine.encoder_forward(self, xv, masks, save=False, out_layers=self.out_layers)
+        B = xv.shape[0] * (1 if masks is None else len(masks))
+        return [o.view(B, -1, self.embed_dim) for o in outs]
+
     def forward_multi(self, x, masks, final_norm=True):
         """All masks in one fused pass.  Returns list of [B, K_i, D] bf16 views (one per mask)."""
         x = self._check_input(x)
@@ -287,6 +296,8 @@ class VisionTransformer(nn.Module):
         """
         if masks is not None and not isinstance(masks, list):
             masks = [masks]
+        if self.out_layers is not None:
+            return self._forward_out_layers(x, masks)
         if masks is None:
             xv = self._check_input(x)
             params = [p for _, p in self.named_parameters()]

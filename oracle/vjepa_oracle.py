@@ -133,14 +133,20 @@ def block(x, S, pre, heads, eps=1e-6):
 # ---------------------------------------------------------------------------------------------
 # networks
 # ---------------------------------------------------------------------------------------------
-def encoder(S, clips, masks, depth, heads, eps=1e-6):
-    """VisionTransformer.forward (src/models/vision_transformer.py:159-195); S uses backbone-level keys."""
+def encoder(S, clips, masks, depth, heads, eps=1e-6, out_layers=None):
+    """VisionTransformer.forward (src/models/vision_transformer.py:159-195); S uses backbone-level keys.
+    out_layers: list of block indices -> list of norm(x) after those blocks (:183-190)."""
     x = patch_embed_3d(clips, S['patch_embed.proj.weight'], S['patch_embed.proj.bias'])
     x = x + S['pos_embed']
     if masks is not None:
         x = apply_masks(x, masks)
+    outs = []
     for i in range(depth):
         x = block(x, S, f'blocks.{i}.', heads, eps)
+        if out_layers is not None and i in out_layers:
+            outs.append(layer_norm(x, S['norm.weight'], S['norm.bias'], eps))
+    if out_layers is not None:
+        return outs
     return layer_norm(x, S['norm.weight'], S['norm.bias'], eps)
 
 
@@ -198,3 +204,35 @@ def ema(S_tgt, S_enc, m):
     with torch.no_grad():
         for k in S_tgt:
             S_tgt[k].mul_(m).add_((1. - m) * S_enc[k].detach())
+
+
+# ---------------------------------------------------------------------------------------------
+# input pipeline  (app/vjepa/transforms.py:86-117,140-153; src/datasets/utils/video/transforms.py:545-577,160-190)
+# ---------------------------------------------------------------------------------------------
+def video_transform(buffer_u8, box, flip, crop_size, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """VideoTransform.__call__ on its non-auto-augment path with the random decisions (crop box, flip) given:
+    uint8 [T,H,W,3] -> float -> [3,T,H,W] -> crop -> bilinear resize (align_corners=False, no antialias; written out
+    explicitly: src = max(0, (dst + 0.5) * in/out - 0.5)) -> flip -> (x - 255 mean) / (255 std).  Returns fp32 [3,T,S,S]."""
+    x = torch.as_tensor(np.asarray(buffer_u8)).to(torch.float32).permute(3, 0, 1, 2)
+    i, j, h, w = box
+    x = x[:, :, i:i + h, j:j + w]
+    S = crop_size
+
+    def axis(n_in):
+        src = (torch.arange(S, dtype=torch.float32) + 0.5) * (torch.tensor(float(n_in)) / float(S)) - 0.5
+        src = torch.clamp(src, min=0.0)
+        i0 = src.floor().to(torch.int64).clamp(max=n_in - 1)
+        i1 = (i0 + 1).clamp(max=n_in - 1)
+        l1 = src - i0.to(torch.float32)
+        return i0, i1, 1.0 - l1, l1
+
+    y0, y1, hy, ly = axis(h)
+    x0, x1, hx, lx = axis(w)
+    top = x[:, :, y0][:, :, :, x0] * hx + x[:, :, y0][:, :, :, x1] * lx
+    bot = x[:, :, y1][:, :, :, x0] * hx + x[:, :, y1][:, :, :, x1] * lx
+    out = hy[:, None] * top + ly[:, None] * bot
+    if flip:
+        out = out.flip(-1)
+    m = torch.tensor(mean, dtype=torch.float32) * 255.
+    s = torch.tensor(std, dtype=torch.float32) * 255.
+    return (out - m[:, None, None, None]) / s[:, None, None, None]

@@ -183,12 +183,12 @@ static void perf(int M, int N, int K, int a_mn, int b_mn, int d_f32, int epi, in
   const int iters = 10;
   for (int i = 0; i < 3; ++i)
     vj_gemm(dA, a_mn ? M : K, a_mn, dB, b_mn ? N : K, b_mn, dD, N, d_f32, M, N, K, dBias, 1.f, epi, dAux, N, 0,
-            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, 0, nullptr);
+            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, split_k != 1, nullptr);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i)
     vj_gemm(dA, a_mn ? M : K, a_mn, dB, b_mn ? N : K, b_mn, dD, N, d_f32, M, N, K, dBias, 1.f, epi, dAux, N, 0,
-            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, 0, nullptr);
+            nullptr, 0, epi == VJ_EPI_GELU_GRAD ? dAux : nullptr, N, split_k, split_k != 1, nullptr);
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms;
@@ -212,6 +212,9 @@ int main(int argc, char** argv) {
       {"mnmn_bn128_wgrad", 256, 384, 1000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, 1, 0, 0},
       {"mnmn_bn256_wgrad_split", 384, 256, 1000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, 3, 1, 0},
       {"mnmn_bn64_wgrad", 192, 192, 520, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, 2, 1, 0},
+      {"mnmn_bn256_wgrad_streamk", 640, 512, 3000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 0},
+      {"mnmn_bn128_wgrad_streamk", 256, 384, 20000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 0},
+      {"kk_bn256_f32_streamk_bias", 520, 512, 1100, 0, 0, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 1},
       {"gelu_auxout", 300, 768, 192, 0, 0, 0, VJ_EPI_GELU, 0, 0, 0, 1, 1, 0, 1},
       {"gelu_noaux", 300, 256, 192, 0, 0, 0, VJ_EPI_GELU, 0, 0, 0, 0, 1, 0, 1},
       {"add_bf16_res", 300, 256, 192, 0, 0, 0, VJ_EPI_ADD, 0, 0, 0, 0, 1, 0, 1},
@@ -240,6 +243,13 @@ int main(int argc, char** argv) {
         {13056, 4096, 1024, 0, 1, 0, VJ_EPI_NONE, 1, "dgrad_ctx"},
         {4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 1, "wgrad_ctx_fc1"},
         {1024, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 4, "wgrad_ctx_proj_split4"},
+        {4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 2, "wgrad_ctx_fc1_split2"},
+        {4096, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, -1, "wgrad_ctx_fc1_streamk"},
+        {3072, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, 2, "wgrad_ctx_qkv_split2"},
+        {3072, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, -1, "wgrad_ctx_qkv_streamk"},
+        {1024, 1024, 13056, 1, 1, 1, VJ_EPI_NONE, -1, "wgrad_ctx_proj_streamk"},
+        {1536, 384, 76032, 1, 1, 1, VJ_EPI_NONE, -1, "fc1_wgrad_pred_streamk"},
+        {384, 1536, 76032, 1, 1, 1, VJ_EPI_NONE, -1, "fc2_wgrad_pred_streamk"},
         {76032, 1536, 384, 0, 0, 0, VJ_EPI_GELU, 1, "fc1_pred"},
         {76032, 1536, 384, 0, 0, 0, VJ_EPI_NONE, 1, "qkv_pred"},
         {76032, 384, 512, 0, 0, 0, VJ_EPI_ADD, 1, "proj_pred"},

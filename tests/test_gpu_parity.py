@@ -633,3 +633,24 @@ def test_flat_grad_statistics_scaler_clip_and_loggers(dev):
     ref = k0.clone(); ref.mul_(0.998).add_((1. - 0.998) * store.flat)
     ks = tgt.backbone._store
     assert torch.equal(ks.flat, ref) and ks._shadow_fresh and torch.equal(ks.shadow, ref.to(torch.bfloat16))
+
+
+def test_out_layers_feature_taps_vs_oracle(dev):
+    """f4 (frozen-encoder inference for the evals): VisionTransformer(out_layers=[...]) returns norm(x) after the chosen
+    blocks (vision_transformer.py:183-190), here against the oracle."""
+    from jepa_b200.models import vit_tiny
+    from oracle import vjepa_oracle as O
+    torch.manual_seed(0)
+    enc = vit_tiny(img_size=224, patch_size=16, num_frames=8, tubelet_size=2, uniform_power=True, out_layers=[5, 8, 11]).to(dev)
+    clips = synth_clips(2, 8, 224, 224, seed=4)
+    with torch.no_grad():
+        outs = enc(clips.to(dev))
+    S = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
+    ref = O.encoder(S, clips, None, 12, 3, out_layers=[5, 8, 11])
+    assert len(outs) == 3 and all(o.shape == (2, 784, 192) for o in outs)
+    for o, r in zip(outs, ref):
+        assert rel_l2(o.float().cpu(), r) < TOL_ACT
+    # the last tap is the ordinary encoder output
+    enc.out_layers = None
+    with torch.no_grad():
+        assert torch.equal(enc(clips.to(dev)), outs[-1])

@@ -62,3 +62,28 @@ def test_fused_mode_agrees_with_plain_restatement(oracle_step):
             assert rel_l2(a, b) < 1e-4
     for n, g in oracle_step["enc_grad"].items():
         assert rel_l2(fused["enc_grad"][n], g) < 2e-3, n
+
+
+def test_input_pipeline_decisions_and_pixels_match_reference(golden_dir):
+    """f3: the host sampler reproduces the reference's crop box / flip bit-exactly (same RNG call order), and the oracle's
+    explicit bilinear restatement reproduces the reference transform's pixels (golden_transforms.pt was produced by the
+    unmodified reference VideoTransform)."""
+    import os
+    import random
+    import numpy as np
+    from jepa_b200.transforms import make_transforms
+    from oracle import vjepa_oracle as O
+    sys_path_note = None  # noqa: F841
+    cases = torch.load(os.path.join(golden_dir, "golden_transforms.pt"))
+    for c in cases:
+        T, H, W = c["shape"]
+        buf = np.random.RandomState(1000 + c["seed"]).randint(0, 256, size=(T, H, W, 3), dtype=np.uint8)
+        tf = make_transforms(random_horizontal_flip=True, random_resize_aspect_ratio=c["ratio"],
+                             random_resize_scale=c["scale"], crop_size=c["crop"])
+        random.seed(c["seed"]); np.random.seed(c["seed"])
+        ticket = tf(buf)
+        assert tuple(ticket.box) == tuple(c["box"]) and ticket.flip == c["flip"], (c["seed"], ticket.box, c["box"])
+        assert torch.equal(ticket.frames, torch.from_numpy(buf))          # the frames travel untouched
+        y = O.video_transform(buf, ticket.box, ticket.flip, c["crop"])
+        assert y.shape == c["out"].shape
+        assert float((y - c["out"]).abs().max()) < 2e-5, c["seed"]
