@@ -262,7 +262,8 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        from jepa_b200.distributed import nccl_pg_options
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device, pg_options=nccl_pg_options())
     lib = _lib.load()
 
     model_name, D, L, heads, crop, frames, B = CONFIGS[args.config]

@@ -36,6 +36,8 @@ const char* vj_last_error_string(void);
 int vj_version(void);
 /* Number of kernels this library has launched so far in this process (monotonic). */
 long long vj_launch_count(void);
+/* CUtensorMap cache statistics: which = 0 -> hits, 1 -> misses (driver encode calls) since the library was loaded. */
+long long vj_tmap_cache_stats(int which);
 
 /* D[M,N] = epi(alpha * A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulate (tcgen05 / TMEM).
  * a_mn = 0: A stored [M,K] (K contiguous, ld = lda);  a_mn = 1: A stored [K,M] (M contiguous).
@@ -173,6 +175,17 @@ int vj_clip_coef(const float* sumsq, int n_seg, float max_norm, float* total_nor
 int vj_scale_flat(float* x, long long n, const float* coef_dev, void* stream);
 /* out[0] += sum(x^2) over a flat fp32 buffer (grad-norm statistics, src/utils/logging.py:91-105). */
 int vj_sumsq(const float* x, long long n, float* out, void* stream);
+
+/* ---- GPU input pipeline -------------------------------------------------------------------------
+ * Decoded uint8 frames -> random-resized crop (bilinear, align_corners = False) -> horizontal flip -> (x - 255 mean) /
+ * (255 std) -> out [B, 3, T, S, S] (fp32 or bf16), one launch per batch.  src_u8: device buffer holding every clip's
+ * frames [T, H_b, W_b, 3]; params: device table, one 40-byte record per clip = {int64 byte offset into src_u8,
+ * int32 H, W, i, j, h, w (crop box), flip, pad}.  mean3 / std3: HOST arrays of 3 floats (0..1 scale).
+ * Replaces VideoTransform.__call__ (app/vjepa/transforms.py:86-117: float conversion, random_resized_crop,
+ * horizontal_flip, _tensor_normalize_inplace :140-153) for the non-auto-augment path; the random decisions are drawn
+ * on the host in the reference's RNG order (jepa_b200/transforms.py). */
+int vj_clip_preprocess(const void* src_u8, const void* params, void* out, int out_f32, int B, int T, int S,
+                       const float* mean3, const float* std3, void* stream);
 
 #ifdef __cplusplus
 }

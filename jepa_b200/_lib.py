@@ -16,6 +16,8 @@ SIGNATURES = {
     "vj_last_error_string": (c_char_p, []),
     "vj_version": (I, []),
     "vj_launch_count": (L, []),
+    "vj_tmap_cache_stats": (L, [I]),
+    "vj_clip_preprocess": (I, [P, P, P, I, I, I, I, P, P, P]),
     "vj_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, I, P, F, I, P, L, I, P, I, P, L, I, I, P]),
     "vj_attn_fwd": (I, [P, P, P, P, I, I, I, I, I, F, P]),
     "vj_attn_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, F, P]),

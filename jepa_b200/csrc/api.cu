@@ -3,6 +3,8 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -54,8 +56,58 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
+// Encoded descriptors are cached (SURVEY 8b allows it: "cached CUtensorMaps keyed by (ptr, shape, stride)"): a train step
+// encodes ~2000 maps, and the caching allocator hands the same addresses back every step, so after the first step a
+// launch costs one hash lookup instead of a driver call per operand.  A map is a pure function of the key.
+struct TmapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  int dtype, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && dtype == o.dtype && swizzle == o.swizzle;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.ld); mix((uint64_t(k.box_inner) << 32) | k.box_outer);
+    mix((uint64_t(uint32_t(k.dtype)) << 32) | uint32_t(k.swizzle));
+    return size_t(h);
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::atomic<long long> g_tmap_hits{0}, g_tmap_misses{0};
+
+static int encode_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                          uint32_t box_inner, uint32_t box_outer, int swizzle);
+
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, uint64_t outer,
                  uint64_t ld_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle) {
+  const TmapKey key{ptr, inner, outer, ld_bytes, box_inner, box_outer, dtype, swizzle};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return 0;
+    }
+  }
+  const int rc = encode_tmap_2d(out, ptr, dtype, inner, outer, ld_bytes, box_inner, box_outer, swizzle);
+  if (rc) return rc;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 16384) g_tmap_cache.clear();   // shapes changing every step (dynamic masks): bounded memory
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+static int encode_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                          uint32_t box_inner, uint32_t box_outer, int swizzle) {
   auto enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -86,3 +138,6 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t inner, u
 extern "C" const char* vj_last_error_string(void) { return vj::g_err; }
 extern "C" int vj_version(void) { return VJ_VERSION; }
 extern "C" long long vj_launch_count(void) { return vj::g_launches.load(std::memory_order_relaxed); }
+extern "C" long long vj_tmap_cache_stats(int which) {
+  return which == 0 ? vj::g_tmap_hits.load(std::memory_order_relaxed) : vj::g_tmap_misses.load(std::memory_order_relaxed);
+}

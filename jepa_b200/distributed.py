@@ -14,6 +14,22 @@ import torch.distributed as dist
 logger = getLogger()
 
 
+def nccl_pg_options():
+    """ProcessGroupNCCL options for the gradient exchange.  The step's GEMM / attention kernels are persistent (one CTA per
+    SM); NCCL's copy/reduce CTAs have to squeeze in between them.  VJ_NCCL_MAX_CTAS / VJ_NCCL_MIN_CTAS / VJ_NCCL_CGA bound
+    how many SMs a collective may occupy (ncclConfig_t maxCTAs / minCTAs / cgaClusterSize); unset = NCCL's defaults."""
+    if not (torch.cuda.is_available() and dist.is_nccl_available()):
+        return None
+    keys = {"VJ_NCCL_MAX_CTAS": "max_ctas", "VJ_NCCL_MIN_CTAS": "min_ctas", "VJ_NCCL_CGA": "cga_cluster_size"}
+    if not any(k in os.environ for k in keys):
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    for env, attr in keys.items():
+        if env in os.environ:
+            setattr(opts.config, attr, int(os.environ[env]))
+    return opts
+
+
 def _active():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
@@ -34,7 +50,8 @@ def init_distributed(port=37123, rank_and_world_size=(None, None)):
     try:
         os.environ['MASTER_PORT'] = str(port)
         backend = 'nccl' if torch.cuda.is_available() else 'gloo'
-        dist.init_process_group(backend=backend, world_size=world_size, rank=rank)
+        dist.init_process_group(backend=backend, world_size=world_size, rank=rank,
+                                pg_options=nccl_pg_options() if backend == 'nccl' else None)
     except Exception as e:
         world_size, rank = 1, 0
         logger.info(f'Rank: {rank}. Distributed training not available {e}')
@@ -123,6 +140,9 @@ class FlatGradSync:
         self.n_calls = 0    # all-reduces issued for the current buffer (tests / launch accounting)
 
     def begin(self, gflat):
+        # a backward that raised after queueing its end-of-backward callback would leave the flag set and make every
+        # later backward skip the stream wait; re-arming here costs at most one redundant (idempotent) callback
+        _callback_queued[0] = False
         self.gflat = gflat
         self.hi = self.lo = gflat.numel()
         self.n_calls = 0
@@ -186,3 +206,9 @@ class DistributedDataParallel(torch.nn.Module):
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
+
+    def no_sync(self):
+        """torch DDP's gradient-accumulation context is NOT supported: every backward writes a fresh flat gradient buffer
+        and all-reduces it in place while the backward is still running, so a second backward before zero_grad() would
+        accumulate into partially reduced data.  The reference never accumulates (app/vjepa/train.py:462-483)."""
+        raise NotImplementedError("jepa_b200 DistributedDataParallel: gradient accumulation / no_sync() is not supported")

@@ -43,6 +43,10 @@ def cu_seqlens_for(segments, device):
     return hit
 
 
+import os as _os
+_STREAM_K = _os.environ.get("VJ_GEMM_STREAMK", "1") != "0"     # "0": first-generation fixed split-K (A/B timing)
+
+
 def _split_k_for(m_out, n_in, k_tokens):
     bn = 256 if n_in % 256 == 0 else (128 if n_in % 128 == 0 else 64)
     tiles = ((m_out + 127) // 128) * (n_in // bn)
@@ -159,7 +163,8 @@ def _wgrad(dy, act, grad_out, bias_grad, tokens):
     n_out, k_in = grad_out.shape
     # stream-K (split_k = -1): 32..128 output tiles for 148 SMs - every SM gets the same number of k-blocks instead of a
     # ragged second wave; all pieces reduce-add into the flat fp32 gradient buffer anyway
-    K.gemm(dy, act, grad_out, a_mn=True, b_mn=True, accumulate=True, split_k=-1)
+    K.gemm(dy, act, grad_out, a_mn=True, b_mn=True, accumulate=True,
+           split_k=-1 if _STREAM_K else _split_k_for(n_out, k_in, tokens))
     if bias_grad is not None:
         K.colsum(dy, bias_grad)
 

@@ -654,3 +654,41 @@ def test_out_layers_feature_taps_vs_oracle(dev):
     enc.out_layers = None
     with torch.no_grad():
         assert torch.equal(enc(clips.to(dev)), outs[-1])
+
+
+def test_clip_preprocess_kernel_vs_reference_fixtures(dev, golden_dir):
+    """f3: uint8 frames -> crop box / flip (host sampler, reference RNG order) -> ONE kernel (bilinear resize, flip,
+    normalise) == the unmodified reference VideoTransform (tests/golden/golden_transforms.pt) and the oracle, per case
+    and batched with different frame sizes per clip; bf16 output = rounded fp32 output."""
+    import random
+    import numpy as np
+    from jepa_b200.transforms import make_transforms, preprocess_batch
+    from oracle import vjepa_oracle as O
+    cases = torch.load(os.path.join(golden_dir, "golden_transforms.pt"))
+    tickets_by_crop = {}
+    for c in cases:
+        T, H, W = c["shape"]
+        buf = np.random.RandomState(1000 + c["seed"]).randint(0, 256, size=(T, H, W, 3), dtype=np.uint8)
+        tf = make_transforms(random_horizontal_flip=True, random_resize_aspect_ratio=c["ratio"],
+                             random_resize_scale=c["scale"], crop_size=c["crop"])
+        random.seed(c["seed"]); np.random.seed(c["seed"])
+        tk = tf(buf)
+        assert tuple(tk.box) == tuple(c["box"]) and tk.flip == c["flip"]
+        y = preprocess_batch([tk], dev, c["crop"])
+        assert y.shape == (1,) + tuple(c["out"].shape) and y.dtype == torch.float32
+        assert float((y[0].cpu() - c["out"]).abs().max()) < 5e-5, c["seed"]
+        assert float((y[0].cpu() - O.video_transform(buf, tk.box, tk.flip, c["crop"])).abs().max()) < 5e-5
+        yb = preprocess_batch([tk], dev, c["crop"], dtype=torch.bfloat16)
+        assert float((yb[0].float().cpu() - c["out"].to(torch.bfloat16).float()).abs().max()) < 2e-2
+        tickets_by_crop.setdefault((c["crop"], T), []).append((tk, c))
+    # a batch of clips with different decoded sizes goes through one launch
+    T = 4
+    mixed = []
+    for seed, (H, W) in enumerate([(48, 64), (36, 100), (70, 50)]):
+        buf = np.random.RandomState(77 + seed).randint(0, 256, size=(T, H, W, 3), dtype=np.uint8)
+        tf = make_transforms(crop_size=32, random_resize_aspect_ratio=(0.75, 1.35), random_resize_scale=(0.3, 1.0))
+        random.seed(seed); np.random.seed(seed)
+        mixed.append((tf(buf), buf))
+    yb = preprocess_batch([t for t, _ in mixed], dev, 32)
+    for b, (tk, buf) in enumerate(mixed):
+        assert float((yb[b].cpu() - O.video_transform(buf, tk.box, tk.flip, 32)).abs().max()) < 5e-5
