@@ -28,6 +28,7 @@ from app.vjepa.transforms import make_transforms
 from app.vjepa.utils import init_opt, init_video_model, load_checkpoint
 from jepa_b200 import step as vj
 from jepa_b200.checkpoint import AsyncCheckpointer
+from jepa_b200.transforms import preprocess_batch
 from src.datasets.data_manager import init_data
 from src.masks.multiblock3d import MaskCollator as MB3DMaskCollator
 from src.masks.random_tube import MaskCollator as TubeMaskCollator
@@ -267,7 +268,11 @@ def main(args, resume_preempt=False):
             assert len(masks_enc) == len(masks_pred), 'Currently require num encoder masks = num predictor masks'
 
             # host -> device; every clip of a sample reuses that sample's mask pair (train.py:391-409)
-            clips = torch.cat([u.to(device, non_blocking=True) for u in udata[0]], dim=0)
+            def to_device(u):
+                if isinstance(u, (list, tuple)):   # ClipTickets: uint8 frames cross PCIe, one kernel crops / flips / normalises
+                    return preprocess_batch(list(u), device, crop_size)
+                return u.to(device, non_blocking=True)
+            clips = torch.cat([to_device(u) for u in udata[0]], dim=0)
             masks_enc = [repeat_interleave_batch(m.to(device, non_blocking=True), batch_size, repeat=num_clips)
                          for m in masks_enc]
             masks_pred = [repeat_interleave_batch(m.to(device, non_blocking=True), batch_size, repeat=num_clips)

@@ -1,13 +1,8 @@
-"""make_transforms with the reference's signature (app/vjepa/transforms.py:15).  The CPU video
-augmentations (random-resized-crop, flip, RandAugment, erasing, normalise) are dataloader work outside
-the accelerated path; synthetic clips are already N(0,1) and crop-sized, so this returns None
-(= identity) and rejects configurations that would silently skip a requested augmentation."""
+"""make_transforms with the reference's signature (app/vjepa/transforms.py:15).
 
-
-def make_transforms(random_horizontal_flip=True, random_resize_aspect_ratio=(3 / 4, 4 / 3),
-                    random_resize_scale=(0.3, 1.0), reprob=0.0, auto_augment=False, motion_shift=False, crop_size=224,
-                    normalize=((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
-    if auto_augment or motion_shift or reprob > 0:
-        raise NotImplementedError("auto_augment / motion_shift / random-erasing are CPU dataloader augmentations "
-                                  "outside this package's scope")
-    return None
+The reference's VideoTransform does its pixel work on CPU dataloader workers.  Here the transform only takes the RANDOM
+DECISIONS (crop box, flip - same RNG call order as the reference) in the worker and returns a ClipTicket with the
+untouched uint8 frames; the pixels are produced on the GPU by one kernel per batch after the uint8 frames crossed PCIe
+(jepa_b200/transforms.py, csrc/preprocess.cu).  auto_augment / motion_shift / random erasing (PIL, per-frame CPU work)
+are rejected rather than silently skipped."""
+from jepa_b200.transforms import make_transforms  # noqa: F401

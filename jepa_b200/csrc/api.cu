@@ -43,6 +43,16 @@ int num_sms() {
   return n;
 }
 
+// SM budget of the PERSISTENT kernels (GEMM, second-generation attention): data-parallel training reserves a few SMs for
+// NCCL's copy / reduce CTAs while gradient buckets are in flight, so that a collective never has to wait for a persistent
+// CTA to retire and a persistent grid never queues behind a resident NCCL CTA (jepa_b200/distributed.py).
+static std::atomic<int> g_sm_limit{0};
+int sm_budget() {
+  const int n = num_sms();
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  return (lim > 0 && lim < n) ? lim : n;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -138,6 +148,10 @@ static int encode_tmap_2d(CUtensorMap* out, const void* ptr, int dtype, uint64_t
 extern "C" const char* vj_last_error_string(void) { return vj::g_err; }
 extern "C" int vj_version(void) { return VJ_VERSION; }
 extern "C" long long vj_launch_count(void) { return vj::g_launches.load(std::memory_order_relaxed); }
+extern "C" int vj_set_sm_limit(int n) {
+  vj::g_sm_limit.store(n < 0 ? 0 : n, std::memory_order_relaxed);
+  return 0;
+}
 extern "C" long long vj_tmap_cache_stats(int which) {
   return which == 0 ? vj::g_tmap_hits.load(std::memory_order_relaxed) : vj::g_tmap_misses.load(std::memory_order_relaxed);
 }

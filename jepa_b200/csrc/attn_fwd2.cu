@@ -449,7 +449,7 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int
   p.scale_log2 = scale * 1.4426950408889634f;
   static int persist = -1;
   if (persist < 0) { const char* e = getenv("VJ_ATTN_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
-  const int grid = (persist && p.n_items > num_sms()) ? num_sms() : p.n_items;
+  const int grid = (persist && p.n_items > sm_budget()) ? sm_budget() : p.n_items;
   kern<<<grid, kFwd2Threads, F::SMEM_BYTES, s>>>(tm, p);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);

@@ -36,6 +36,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+int sm_budget();          // num_sms() minus the SMs currently reserved for NCCL (vj_set_sm_limit)
 void count_launch(int n);  // bookkeeping for vj_launch_count()
 
 // Encode a 2-D tiled tensor map.  `inner`/`outer` are element counts, `ld_bytes` the byte

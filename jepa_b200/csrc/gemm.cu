@@ -578,7 +578,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
     configured = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
-  int grid = total < num_sms() ? total : num_sms();
+  int grid = total < sm_budget() ? total : sm_budget();
   if (p.stream_k) {
     const long long total_kb = (long long)p.tiles_m * p.tiles_n * p.kb_total;
     grid = int((total_kb + p.sk_chunk - 1) / p.sk_chunk);
@@ -662,7 +662,7 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.sk_chunk = 0;
   if (split_k < 0) {
     const long long total_kb = (long long)p.tiles_m * p.tiles_n * p.kb_total;
-    const long long ctas = total_kb < num_sms() ? total_kb : num_sms();
+    const long long ctas = total_kb < sm_budget() ? total_kb : sm_budget();
     p.stream_k = 1;
     p.sk_chunk = (total_kb + ctas - 1) / ctas;
     split_k = 1;

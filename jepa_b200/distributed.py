@@ -111,6 +111,21 @@ class AllReduce(torch.autograd.Function):
 # -------------------------------------------------------------------------------------------------
 _pending = []           # NCCL work handles of all-reduces issued during the current backward pass
 _callback_queued = [False]
+_SM_RESERVE = int(os.environ.get("VJ_SM_RESERVE", "0"))   # SMs left to NCCL while gradient buckets are in flight
+
+
+def _set_sm_reserve(on):
+    """Shrink (or restore) the grid of the persistent GEMM / attention kernels by VJ_SM_RESERVE SMs: NCCL's CTAs then
+    always find a free SM and a persistent grid never queues behind a resident NCCL CTA (pair with VJ_NCCL_MAX_CTAS)."""
+    if _SM_RESERVE <= 0 or not torch.cuda.is_available():
+        return
+    try:
+        from . import _lib
+        fn = _lib.load().vj_set_sm_limit
+    except Exception:
+        return
+    n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    fn(int(max(1, n - _SM_RESERVE)) if on else 0)
 
 
 def _wait_pending():
@@ -118,6 +133,7 @@ def _wait_pending():
     _callback_queued[0] = False
     while _pending:
         _pending.pop().wait()
+    _set_sm_reserve(False)
 
 
 class FlatGradSync:
@@ -143,6 +159,7 @@ class FlatGradSync:
         # a backward that raised after queueing its end-of-backward callback would leave the flag set and make every
         # later backward skip the stream wait; re-arming here costs at most one redundant (idempotent) callback
         _callback_queued[0] = False
+        _set_sm_reserve(True)
         self.gflat = gflat
         self.hi = self.lo = gflat.numel()
         self.n_calls = 0

@@ -211,11 +211,12 @@ def blocks_backward(spec, weights, saved, dx, seq, store, gflat, scratch, sync=N
             _wgrad(dqkv, s.ln1, gv(pre + "attn.qkv.weight"), gv(pre + "attn.qkv.bias"), T)
         else:
             pw = scratch.get("pad_grad")
-            if pw is None:
-                pw = (_empty((D, H * hdp), F32, dev), _empty((3 * H * hdp, D), F32, dev), _empty((3 * H * hdp,), F32, dev))
+            if pw is None:   # three padded fp32 gradient scratch tensors carved out of ONE buffer: one memset per layer
+                n0, n1, n2 = D * H * hdp, 3 * H * hdp * D, 3 * H * hdp
+                flat = _empty((n0 + n1 + n2,), F32, dev)
+                pw = (flat[:n0].view(D, H * hdp), flat[n0:n0 + n1].view(3 * H * hdp, D), flat[n0 + n1:].view(3 * H * hdp), flat)
                 scratch["pad_grad"] = pw
-            for t in pw:
-                t.zero_()
+            pw[3].zero_()
             _wgrad(dx_mid, s.attn, pw[0], gv(pre + "attn.proj.bias"), T)
             _wgrad(dqkv, s.ln1, pw[1], pw[2], T)
             K.head_pad(pw[0], gv(pre + "attn.proj.weight"), D, H, hd, hdp, 1, unpad_add=True)

@@ -105,3 +105,17 @@ print(json.dumps(dict(ok=True, n_enc=len(ck['encoder']), n_pred=len(ck['predicto
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", env=env, timeout=300)
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
         assert json.loads(r.stdout.strip().splitlines()[-1])["ok"]
+
+
+def test_app_main_with_gpu_input_pipeline(tmp_path):
+    """f3 end to end: dataset_type synthetic_uint8 feeds decoded-video-like uint8 frames through the reference-shaped
+    transform (decisions on the host, RNG order of the reference) and the crop / flip / normalise kernel into the step."""
+    assert torch.cuda.is_available()
+    from app.scaffold import main as app_main
+    cfg = _cfg(tmp_path, epochs=1, load=False)
+    cfg["data"]["dataset_type"] = "synthetic_uint8"
+    cfg["optimization"]["ipe"] = 2
+    app_main("vjepa", cfg)
+    body = [r for r in _rows(tmp_path) if r and r[0] != "epoch"]
+    assert [r[:2] for r in body] == [["1", "0"], ["1", "1"]]
+    assert all(0.1 < float(r[2]) < 3.0 for r in body), body
