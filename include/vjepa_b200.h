@@ -36,6 +36,9 @@ const char* vj_last_error_string(void);
 int vj_version(void);
 /* Number of kernels this library has launched so far in this process (monotonic). */
 long long vj_launch_count(void);
+/* Cap the grid of the PERSISTENT kernels (GEMM, second-generation attention) at n SMs (n <= 0: all SMs).  Data-parallel
+ * training leaves a few SMs to NCCL's CTAs while gradient buckets are in flight (jepa_b200/distributed.py). */
+int vj_set_sm_limit(int n);
 /* CUtensorMap cache statistics: which = 0 -> hits, 1 -> misses (driver encode calls) since the library was loaded. */
 long long vj_tmap_cache_stats(int which);
 

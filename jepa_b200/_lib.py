@@ -17,6 +17,7 @@ SIGNATURES = {
     "vj_version": (I, []),
     "vj_launch_count": (L, []),
     "vj_tmap_cache_stats": (L, [I]),
+    "vj_set_sm_limit": (I, [I]),
     "vj_clip_preprocess": (I, [P, P, P, I, I, I, I, P, P, P]),
     "vj_gemm": (I, [P, L, I, P, L, I, P, L, I, I, I, I, P, F, I, P, L, I, P, I, P, L, I, I, P]),
     "vj_attn_fwd": (I, [P, P, P, P, I, I, I, I, I, F, P]),

@@ -18,10 +18,12 @@
 //     by the two key tiles; K / V of the next work item are prefetched while the current one finishes;
 //   * query tiles past the end of the sequence tail skip their exponentials and dV / dK reduction steps.
 //
-//   warp 0        TMA producer (+ stages lse2 / delta rows of every query tile in a 2-deep smem ring)
-//   warp 1        MMA issuer
-//   warps 2-9     softmax group of key tile 0: warp (qd, half) = key rows qd*32.. x query columns half*64..+64
-//   warps 10-17   softmax group of key tile 1
+//   warps 0-7     softmax group of key tile 0: warp (qd, half) = key rows qd*32.. x query columns half*64..+64
+//   warps 8-15    softmax group of key tile 1
+//   warp 16       TMA producer (+ stages lse2 / delta rows of every query tile in a 2-deep smem ring)
+//   warp 17       MMA issuer: one thread issues all ~56 MMAs of a tile pair (most of them N = 32, i.e. 16 tensor clocks
+//                 each) - it owns the highest warp id (first pick of its scheduler) and only adds compile-time offsets to
+//                 per-tile descriptors; every k-step loop is fully unrolled with a predicate
 // TMEM (512 columns): S^T/dP^T of kt 0 | of kt 1 | dV0 dK0 dV1 dK1 | dQ[2] (ping-pong over query tiles).
 #include <stdlib.h>
 
@@ -38,6 +40,7 @@ struct AttnBwd2Params {
   const float* delta;
   __nv_bfloat16* dqkv;
   int H, T, nseq, kpairs, n_items;
+  int pingpong;     // 1: the two groups take turns in the exp pass; 0: free running
   float scale, scale_log2;
 };
 
@@ -102,8 +105,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     }
     fence_mbar_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ); }
-  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 16 && lane == 0) { tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ); }
+  if (warp == 17) tmem_alloc<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -126,7 +129,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     return true;
   };
 
-  if (warp == 0) {
+  if (warp == 16) {
     // ------------------------------------------------------------------------------ TMA producer + statistics
     int uk0 = 0, uk1 = 0;          // K/V loads so far per key tile
     int qi = 0;                    // query tiles streamed so far (Q/dO stage = qi & 1, statistics slot = qi & 1)
@@ -198,17 +201,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_128 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_hd = make_idesc_bf16(128, HD, 0, 1);
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);
+      const uint64_t dQk0 = kmajor_base<HD>(sQDO), dQmn0 = mnmajor_base<HD>(sQDO);   // stage 0 of the Q / dO ring
+      const uint64_t dDS0 = make_smem_desc(sDS, 16384, 1024, 2);
       int uk0 = 0, uk1 = 0, qi = 0, c0 = 0, c1 = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         Item it;
         if (!decode(item, it)) continue;
-        uint32_t kaddr[2] = {0, 0};
+        uint64_t dKk[2] = {0, 0}, dVk[2] = {0, 0}, dKmn[2] = {0, 0};   // K / V tiles as K-major A operands, K as MN-major B
         int kbuf[2] = {0, 0};
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt) {
@@ -216,16 +221,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           const int uk = kt ? uk1 : uk0;
           kbuf[kt] = uk & 1;
           mbar_wait(kv_full(kbuf[kt], kt), uint32_t(uk >> 1) & 1);
-          kaddr[kt] = sKV + (kbuf[kt] * 2 + kt) * 2 * TILE;
+          const uint32_t ka = sKV + (kbuf[kt] * 2 + kt) * 2 * TILE;
+          dKk[kt] = kmajor_base<HD>(ka);
+          dVk[kt] = kmajor_base<HD>(ka + TILE);
+          dKmn[kt] = mnmajor_base<HD>(ka);
         }
         if (it.n_kt > 0) uk0++;
         if (it.n_kt > 1) uk1++;
         auto issue_S = [&](int kt, int st) {   // S^T = K Q^T (M = keys, N = queries); overwrites the dS^T columns
           const uint32_t tST = tmem_base + (kt ? B::TM_ST1 : B::TM_ST0);
-          const uint32_t sQi = sQDO + st * 2 * TILE;
+          const uint64_t dq = desc_advance(dQk0, uint32_t(st) * 2 * TILE);
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk)
-            umma_f16(tST, kmajor_desc<HD>(kaddr[kt], kk), kmajor_desc<HD>(sQi, kk), idesc_128, kk > 0);
+            umma_f16(tST, desc_advance(dKk[kt], kmajor_koff<HD>(kk)), desc_advance(dq, kmajor_koff<HD>(kk)), idesc_128, kk > 0);
           umma_commit(s_full(kt));
         };
         mbar_wait(qdo_full(qi & 1), uint32_t(qi >> 1) & 1);
@@ -235,7 +243,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           if (kt < it.n_kt) issue_S(kt, qi & 1);
         for (int i = 0; i < it.n_q; ++i, ++qi) {
           const int st = qi & 1;
-          const uint32_t sQi = sQDO + st * 2 * TILE, sDOi = sQi + TILE;
+          const uint64_t dQk = desc_advance(dQk0, uint32_t(st) * 2 * TILE), dQmn = desc_advance(dQmn0, uint32_t(st) * 2 * TILE);
+          const uint64_t dDOk = desc_advance(dQk, TILE), dDOmn = desc_advance(dQmn, TILE);
           const int qv = min(128, it.len - i * 128);
           const int qsteps = (qv + 15) >> 4;          // reduction steps over the valid queries of this tile
           const uint32_t tDQ = tmem_base + ((qi & 1) ? B::TM_DQ1 : B::TM_DQ0);
@@ -246,36 +255,43 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             const uint32_t tST = tmem_base + (kt ? B::TM_ST1 : B::TM_ST0);
             const uint32_t tDV = tmem_base + (kt ? B::TM_DV1 : B::TM_DV0);
             const uint32_t tDK = tmem_base + (kt ? B::TM_DK1 : B::TM_DK0);
-            const uint32_t sK = kaddr[kt], sV = kaddr[kt] + TILE;
             const int kvalid = min(128, it.len - it.kv0 - kt * 128);
+            const int ksteps = (kvalid + 15) >> 4;
             // ---- P^T written: dV += P^T dO_i (A = P^T from TMEM, in place over the S^T columns: queries 0..63 sit in
             // columns 0..31, 64..127 in columns 64..95), then dP^T = V dO_i^T over the same columns - tcgen05.mma
             // executes in issue order, so P^T has been consumed before it is overwritten
             mbar_wait(p_full(kt), uint32_t(cc) & 1);
             tc_fence_after();
-            for (int kk = 0; kk < qsteps; ++kk)
-              umma_f16_ts(tDV, tST + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              if (kk < qsteps)
+                umma_f16_ts(tDV, tST + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dDOmn, mnmajor_koff<HD>(kk)), idesc_hd,
+                            (i > 0 || kk > 0));
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk)
-              umma_f16(tST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
+              umma_f16(tST, desc_advance(dVk[kt], kmajor_koff<HD>(kk)), desc_advance(dDOk, kmajor_koff<HD>(kk)), idesc_128, kk > 0);
             umma_commit(dp_full(kt));
             // ---- dS^T written (TMEM in place over dP^T, and shared memory): dK += dS^T Q_i ; S^T of the next query
             // tile (after dK in issue order: it overwrites dS^T) ; dQ_i (+)= dS K
             mbar_wait(ds_full(kt), uint32_t(cc) & 1);
             tc_fence_after();
-            for (int kk = 0; kk < qsteps; ++kk)
-              umma_f16_ts(tDK, tST + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              if (kk < qsteps)
+                umma_f16_ts(tDK, tST + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dQmn, mnmajor_koff<HD>(kk)), idesc_hd,
+                            (i > 0 || kk > 0));
             if (i + 1 < it.n_q) {
               if (kt == 0) { mbar_wait(qdo_full((qi + 1) & 1), uint32_t((qi + 1) >> 1) & 1); tc_fence_after(); }
               issue_S(kt, (qi + 1) & 1);
             }
             if (kt == 0 && qi >= 2) { mbar_wait(dq_free(qi & 1), uint32_t((qi >> 1) - 1) & 1); tc_fence_after(); }
             {
-              const uint32_t ds_tile = sDS + kt * C::P_BYTES;
-              const int ksteps = (kvalid + 15) >> 4;
-              for (int kk = 0; kk < ksteps; ++kk)   // A = dS^T tile read M-major (queries contiguous), B = K MN-major
-                umma_f16(tDQ, make_smem_desc(ds_tile + kk * 2048, 16384, 1024, 2), mnmajor_desc<HD>(sK, kk), idesc_dq,
-                         (kt > 0 || kk > 0));
+              const uint64_t dds = desc_advance(dDS0, uint32_t(kt) * C::P_BYTES);   // dS^T tile read M-major (queries contiguous)
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                if (kk < ksteps)
+                  umma_f16(tDQ, desc_advance(dds, uint32_t(kk) * 2048), desc_advance(dKmn[kt], mnmajor_koff<HD>(kk)), idesc_dq,
+                           (kt > 0 || kk > 0));
             }
             umma_commit(ps_free(kt));
             if (kt == it.n_kt - 1) { umma_commit(dq_done(qi & 1)); umma_commit(qdo_free(st)); }
@@ -290,8 +306,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     __syncwarp();
   } else {
     // ------------------------------------------------------------------------------ softmax groups
-    const int g = (warp - 2) >> 3;            // group = key tile
-    const int wg = (warp - 2) & 7;            // warp inside the group
+    const int g = warp >> 3;                  // group = key tile
+    const int wg = warp & 7;                  // warp inside the group
     const int qd = warp & 3;                  // TMEM lane quarter
     const int half = wg >> 2;                 // query-column half (needs wg's low bits to cover all four quarters)
     const int r = qd * 32 + lane;             // key row inside the tile
@@ -302,7 +318,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint32_t tST = tmem_base + (g ? B::TM_ST1 : B::TM_ST0) + lane_addr;
     const int col0 = half * 64;
     const int my_bar = 2 + g, other_bar = 3 - g;
-    if (g == 1) bar_arrive_n(2, 512);         // group 0 runs the first exp pass
+    if (g == 1 && p.pingpong) bar_arrive_n(2, 512);   // group 0 runs the first exp pass
     int c = 0;                                // iterations done by this group (phases of s/p/dp/ds/ps_free)
     int qi = 0;                               // query tiles seen by the CTA (statistics slot, dQ buffer)
     auto drain_dq = [&](const Item& it, int qtile, int q_index) {   // dQ partial of a finished query tile -> global fp32
@@ -330,7 +346,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       Item it;
       if (!decode(item, it)) continue;
       if (g >= it.n_kt) { qi += it.n_q; continue; }
-      const bool pingpong = it.n_kt == 2;
+      const bool pingpong = it.n_kt == 2 && p.pingpong;
       const bool drainer = (g == it.n_kt - 1) && half == 0;   // the group whose dQ MMA completes the partial drains it
       const int kv_row0 = it.kv0 + g * 128;
       const uint32_t kvmask = (kv_row0 + r < it.len) ? 0xFFFFFFFFu : 0u;
@@ -455,7 +471,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
 // small helper kernels shared with the first generation (defined in attn_bwd.cu)
@@ -488,8 +504,10 @@ int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const f
   p.H = H; p.T = T; p.nseq = nseq; p.kpairs = (max_len + 255) / 256;
   p.n_items = p.kpairs * nseq * H;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  static int persist = -1;
+  static int persist = -1, pingpong = -1;
   if (persist < 0) { const char* e = getenv("VJ_ATTN_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+  if (pingpong < 0) { const char* e = getenv("VJ_ATTN_PINGPONG"); pingpong = (e && e[0] == '0') ? 0 : 1; }
+  p.pingpong = pingpong;
   const int grid = (persist && p.n_items > sm_budget()) ? sm_budget() : p.n_items;
   kern<<<grid, kBwd2Threads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
   VJ_CUDA(cudaGetLastError());

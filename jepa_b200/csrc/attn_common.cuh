@@ -42,6 +42,24 @@ VJ_DEVINL uint64_t mnmajor_desc(uint32_t tile, int kk) {
   using C = AttnCfg<HD>;
   return make_smem_desc(tile + kk * C::MN_KSTEP, C::BOX_BYTES, C::SBO, C::LAYOUT);
 }
+// Byte offsets of k-step kk inside a tile (compile-time when kk is an unrolled loop index): the MMA-issuing thread builds
+// one descriptor per operand tile and only ADDS these (>> 4) to its address field - a tcgen05.mma then costs a couple of
+// integer instructions to issue instead of a descriptor construction (a single thread issues every MMA of the CTA).
+template <int HD>
+VJ_DEVINL constexpr uint32_t kmajor_koff(int kk) {
+  using C = AttnCfg<HD>;
+  return uint32_t((kk / (C::BOX_INNER / 16)) * C::BOX_BYTES + (kk % (C::BOX_INNER / 16)) * 32);
+}
+template <int HD>
+VJ_DEVINL constexpr uint32_t mnmajor_koff(int kk) { return uint32_t(kk * AttnCfg<HD>::MN_KSTEP); }
+template <int HD>
+VJ_DEVINL uint64_t kmajor_base(uint32_t tile) { return make_smem_desc(tile, 16, AttnCfg<HD>::SBO, AttnCfg<HD>::LAYOUT); }
+template <int HD>
+VJ_DEVINL uint64_t mnmajor_base(uint32_t tile) {
+  return make_smem_desc(tile, AttnCfg<HD>::BOX_BYTES, AttnCfg<HD>::SBO, AttnCfg<HD>::LAYOUT);
+}
+VJ_DEVINL uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + uint64_t(bytes >> 4); }
+
 // P / dS tile: [128 rows x 128 reduction] bf16, K-major, two 128B-swizzled atoms of 64 columns
 VJ_DEVINL uint64_t ptile_desc(uint32_t tile, int kk) {
   return make_smem_desc(tile + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2);

@@ -45,15 +45,6 @@ struct GemmParams {
   int has_auxout;
   int reduce_add;
   float alpha;
-  // bf16 outputs leave the epilogue as plain 16-byte global stores straight from registers (thread = row, 64 contiguous
-  // bytes per 32-column chunk) instead of st.shared + fence.proxy.async + TMA store + wait_group: that serial chain costs
-  // ~370 of the ~810 clk per chunk and makes the short-K (predictor, K = 384) GEMMs epilogue-bound.  fp32 / reduce-add
-  // outputs keep the TMA path (the reduction happens in the TMA unit).
-  int direct_store;
-  void* dptr;
-  long long ldd;
-  void* xptr;               // second bf16 output of the GELU epilogues
-  long long ldx;
   unsigned lbo_k, sbo_k, lbo_mn, sbo_mn;   // smem-descriptor strides (bytes) of the K-major / MN-major operand tiles
 };
 
@@ -483,17 +474,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           __syncwarp();
         }
-        const bool direct = !OUT_F32 && p.direct_store;
-        const int grow_d = row0 + lane;                         // this thread's output row (direct stores)
         bool two_stores = false;
         if (EPI == VJ_EPI_GELU || EPI == VJ_EPI_GELU_GRAD) {
           // second output (needed by the backward) leaves through bufB, gelu(pre) through bufA, one bulk group:
           //   VJ_EPI_GELU      : aux_out = pre-activation
           //   VJ_EPI_GELU_GRAD : aux_out = gelu'(pre) = Phi(pre) + pre * pdf(pre)  (shares the erf with gelu itself, so
           //                      the backward's epilogue is a plain multiply instead of a second erf / exp evaluation)
+          // (plain 16-byte global stores straight from registers - thread = row - were measured instead of the staged TMA
+          //  stores: 32 rows x 16 B per instruction are partial-sector writes, qkv_pred fell from 1035 to 629 TF/s.)
           const bool second = p.has_auxout && !OUT_F32;
-          if (second && !direct) wait_prev_store();
-          uint4* xrow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.xptr) + (long long)grow_d * p.ldx + n0 + col0);
+          if (second) wait_prev_store();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float d[8];
@@ -504,27 +494,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               uint4 o;
               o.x = pack_bf16x2(d[0], d[1]); o.y = pack_bf16x2(d[2], d[3]);
               o.z = pack_bf16x2(d[4], d[5]); o.w = pack_bf16x2(d[6], d[7]);
-              if (direct) { if (grow_d < p.M) xrow[j] = o; }
-              else sts128(bufB + swz_off(lane, j, false), o);
+              sts128(bufB + swz_off(lane, j, false), o);
             }
           }
-          two_stores = second && !direct;
-        }
-
-        if (direct) {
-          if (grow_d < p.M) {
-            uint4* drow = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dptr) + (long long)grow_d * p.ldd + n0 + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              drow[j] = o;
-            }
-          }
-          continue;
+          two_stores = second;
         }
 
         wait_prev_store();
@@ -678,13 +651,6 @@ extern "C" int vj_gemm(const void* A, long long lda, int a_mn, const void* B, lo
   p.reduce_add = (accumulate || p.split_k > 1 || p.stream_k) ? 1 : 0;
   p.alpha = alpha;
   p.lbo_k = 16; p.sbo_k = 1024; p.lbo_mn = 8192; p.sbo_mn = 1024;
-  {
-    static int direct = -1;   // VJ_GEMM_DIRECT=0: bf16 outputs through smem staging + TMA stores (first generation)
-    if (direct < 0) { const char* e = getenv("VJ_GEMM_DIRECT"); direct = (e && e[0] == '0') ? 0 : 1; }
-    p.direct_store = direct;
-  }
-  p.dptr = D; p.ldd = ldd;
-  p.xptr = aux_out; p.ldx = ldauxout;
 
   CUtensorMap tA, tB, tD, tX;
   int rc;

@@ -207,7 +207,7 @@ class VisionTransformer(nn.Module):
         self._spec = engine.StackSpec(embed_dim, num_heads, int(embed_dim * mlp_ratio), depth, "blocks")
 
     def _load_from_state_dict(self, *args, **kwargs):
-        super()._load_from_state_dict(*args, **kwargs)
+        nn.Module._load_from_state_dict(self, *args, **kwargs)   # (explicit base: the predictor class reuses this function)
         self._store.invalidate_shadow()      # parameters changed behind the optimizer's back: re-cast the bf16 operands
 
     def __deepcopy__(self, memo):

@@ -214,7 +214,7 @@ int main(int argc, char** argv) {
       {"mnmn_bn64_wgrad", 192, 192, 520, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, 2, 1, 0},
       {"mnmn_bn256_wgrad_streamk", 640, 512, 3000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 0},
       {"mnmn_bn128_wgrad_streamk", 256, 384, 20000, 1, 1, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 0},
-      {"kk_bn256_f32_streamk_bias", 520, 512, 1100, 0, 0, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 1},
+      {"kk_bn256_f32_streamk_bias", 520, 512, 1104, 0, 0, 1, VJ_EPI_NONE, 0, 0, 0, 0, -1, 1, 1},
       {"gelu_auxout", 300, 768, 192, 0, 0, 0, VJ_EPI_GELU, 0, 0, 0, 1, 1, 0, 1},
       {"gelu_noaux", 300, 256, 192, 0, 0, 0, VJ_EPI_GELU, 0, 0, 0, 0, 1, 0, 1},
       {"add_bf16_res", 300, 256, 192, 0, 0, 0, VJ_EPI_ADD, 0, 0, 0, 0, 1, 0, 1},

@@ -406,10 +406,17 @@ def test_wgrad_split_k_full_token_counts(dev, T, n_out, k_in):
     r0, c0 = n_out - 256, max(0, k_in - 256 - 64)
     ref = base[r0:r0 + 256, c0:c0 + 256].double() + dy[:, r0:r0 + 256].double().t() @ x[:, c0:c0 + 256].double()
     got = dw[r0:r0 + 256, c0:c0 + 256].cpu()
-    assert rel_l2(got, ref) < 2e-6, (sk, rel_l2(got, ref))
+    e = rel_l2(got, ref)
+    print(f"wgrad T={T} {n_out}x{k_in} split_k={sk}: rel-L2 vs fp64 {e:.3e}")
+    assert e < 2e-5, (sk, e)             # fp32 tensor-core accumulation over up to 76 032 products per output
+    # stream-K decomposition of the same GEMM (split_k = -1): identical result up to summation order
+    dw2 = base.clone().to(dev)
+    Kn.gemm(dy.to(dev, torch.bfloat16), x.to(dev, torch.bfloat16), dw2, a_mn=True, b_mn=True, accumulate=True, split_k=-1)
+    assert rel_l2(dw2[r0:r0 + 256, c0:c0 + 256].cpu(), ref) < 2e-5
     db = torch.zeros(n_out, device=dev)
     Kn.colsum(dy.to(dev, torch.bfloat16), db)
-    assert rel_l2(db.cpu(), dy.double().sum(0)) < 1e-5
+    e2 = rel_l2(db.cpu(), dy.double().sum(0))
+    assert e2 < 1e-4, e2
 
 
 def test_step_with_token_counts_not_multiple_of_8(dev):
