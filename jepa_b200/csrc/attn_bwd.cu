@@ -586,12 +586,12 @@ template <int HD>
 int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
                      float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale, cudaStream_t s);
 
-// VJ_ATTN_BWD=1 selects the first-generation kernels for every head dim (A/B timing)
+// Default = first-generation kernels for every head dim; VJ_ATTN_BWD=2 selects attn_bwd2.cu (head dim 32) for A/B runs.
 static int attn_bwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_BWD");
-    gen = (e && e[0] == '1') ? 1 : 2;
+    gen = (e && e[0] == '2') ? 2 : 1;
   }
   return gen;
 }

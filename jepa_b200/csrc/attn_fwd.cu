@@ -345,12 +345,14 @@ template <int HD>
 int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
                      float scale, cudaStream_t s);
 
-// VJ_ATTN_FWD=1 selects the first-generation kernel (one query tile per CTA, two CTAs per SM) - kept for A/B timing
+// Default = first generation (one query tile per CTA, two CTAs per SM): measured faster on B200 at every BASELINE shape
+// (hd 64, S = 1568: 0.560 ms vs 0.646 ms free-running / 0.685 ms ping-pong for the persistent kernel, profiles/r02_*).
+// VJ_ATTN_FWD=2 selects the second-generation kernel for A/B timing.
 static int attn_fwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_FWD");
-    gen = (e && e[0] == '1') ? 1 : 2;
+    gen = (e && e[0] == '2') ? 2 : 1;
   }
   return gen;
 }
