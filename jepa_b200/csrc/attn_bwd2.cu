@@ -41,6 +41,7 @@ struct AttnBwd2Params {
   __nv_bfloat16* dqkv;
   int H, T, nseq, kpairs, n_items;
   int pingpong;     // 1: the two groups take turns in the exp pass; 0: free running
+  int debug;        // VJ_BWD2_DEBUG bring-up switches
   float scale, scale_log2;
 };
 
@@ -287,11 +288,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
             if (kt == 0 && qi >= 2) { mbar_wait(dq_free(qi & 1), uint32_t((qi >> 1) - 1) & 1); tc_fence_after(); }
             {
               const uint64_t dds = desc_advance(dDS0, uint32_t(kt) * C::P_BYTES);   // dS^T tile read M-major (queries contiguous)
+              if (p.debug == 1) {   // bring-up: descriptors rebuilt per k-step exactly as attn_bwd.cu does
+                const uint32_t ds_tile = sDS + kt * C::P_BYTES;
+                const uint32_t ka = sKV + (kbuf[kt] * 2 + kt) * 2 * TILE;
+                for (int kk = 0; kk < ksteps; ++kk)
+                  umma_f16(tDQ, make_smem_desc(ds_tile + kk * 2048, 16384, 1024, 2), mnmajor_desc<HD>(ka, kk), idesc_dq,
+                           (kt > 0 || kk > 0));
+              } else {
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
                 if (kk < ksteps)
                   umma_f16(tDQ, desc_advance(dds, uint32_t(kk) * 2048), desc_advance(dKmn[kt], mnmajor_koff<HD>(kk)), idesc_dq,
                            (kt > 0 || kk > 0));
+              }
             }
             umma_commit(ps_free(kt));
             if (kt == it.n_kt - 1) { umma_commit(dq_done(qi & 1)); umma_commit(qdo_free(st)); }
@@ -508,6 +517,7 @@ int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const f
   if (persist < 0) { const char* e = getenv("VJ_ATTN_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
   if (pingpong < 0) { const char* e = getenv("VJ_ATTN_PINGPONG"); pingpong = (e && e[0] == '0') ? 0 : 1; }
   p.pingpong = pingpong;
+  { const char* e = getenv("VJ_BWD2_DEBUG"); p.debug = e ? atoi(e) : 0; }
   const int grid = (persist && p.n_items > sm_budget()) ? sm_budget() : p.n_items;
   kern<<<grid, kBwd2Threads, B::SMEM_BYTES, s>>>(tq, tdo, tdq, p);
   VJ_CUDA(cudaGetLastError());

@@ -99,4 +99,33 @@ VJ_DEVINL void store_rows_bf16(uint32_t stage, const float (&vals)[HD], float mu
 }
 
 
+// 32 scores -> p = 2^(s*scale - moff), packed fp32x2 scale/subtract and row sums, bf16 pairs stored to TMEM four columns
+// (eight probabilities) at a time.  MASK: columns >= valid (absolute index base + i) produce exactly 0.
+// POLY of every 8 exponentials run on the FMA / ALU pipes (ex2_poly) instead of MUFU, the pipe that bounds softmax.
+// Only the 8-column groups G0 <= g < G1 are processed (lets the caller interleave a tcgen05.ld between two halves).
+template <bool MASK, int POLY = 0, int G0 = 0, int G1 = 4>
+VJ_DEVINL void exp_store32(const uint32_t (&sv)[32], int base, int valid, uint64_t scale2, uint64_t nmoff2, uint64_t& lsum,
+                           uint32_t tmem_p) {
+#pragma unroll
+  for (int g = G0; g < G1; ++g) {
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 8 * g + 2 * k;
+      float xa, xb;
+      upk2(fma2(pk2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), scale2, nmoff2), xa, xb);
+      float a = ((i & 7) >= 8 - POLY) ? ex2_poly(xa) : ex2_approx(xa);
+      float b = (((i + 1) & 7) >= 8 - POLY) ? ex2_poly(xb) : ex2_approx(xb);
+      if (MASK) {
+        a = (base + i < valid) ? a : 0.f;
+        b = (base + i + 1 < valid) ? b : 0.f;
+      }
+      lsum = add2(lsum, pk2(a, b));
+      o[k] = pack_bf16x2(a, b);
+    }
+    tmem_st4(tmem_p + g * 4, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+
 }  // namespace vj

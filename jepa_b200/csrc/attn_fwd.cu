@@ -345,14 +345,24 @@ template <int HD>
 int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
                      float scale, cudaStream_t s);
 
-// Default = first generation (one query tile per CTA, two CTAs per SM): measured faster on B200 at every BASELINE shape
-// (hd 64, S = 1568: 0.560 ms vs 0.646 ms free-running / 0.685 ms ping-pong for the persistent kernel, profiles/r02_*).
-// VJ_ATTN_FWD=2 selects the second-generation kernel for A/B timing.
+// Default: attn_fwd4.cu (64-key tiles, four small serial CTAs per SM) for head dims 32 / 64, this file's kernel (one query
+// tile, 128-key tiles, two CTAs per SM) for head dim 128.  Measured on B200, 16 heads x 32 sequences (tests/native/test_attn
+// fwdbig, profiles/r02_attn_fwd_variants.txt): hd 64 S=1568: gen1 0.560 ms, persistent two-tile ping-pong (attn_fwd2.cu)
+// 0.685 / 0.646 ms, eight softmax warps (attn_fwd3.cu) 0.567 ms, fwd4 0.474 ms; hd 32 S=1184: 0.319 / 0.365 / 0.323 / 0.268.
+// VJ_ATTN_FWD=1|2|3|4|5 forces one generation for A/B timing (5 = fwd4 with three CTAs per SM).
+// VJ_ATTN_FWD=3 selects attn_fwd3.cu (gen-1 CTA with eight softmax warps, two threads per query row).
+template <int HD>
+int launch_attn_fwd3(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
+                     float scale, cudaStream_t s);
+// VJ_ATTN_FWD=4 / 5 select attn_fwd4.cu (64-key tiles, fully serial CTAs, four / three of them per SM; head dims 32, 64).
+template <int HD, int NCTA>
+int launch_attn_fwd4(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
+                     float scale, cudaStream_t s);
 static int attn_fwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_FWD");
-    gen = (e && e[0] == '2') ? 2 : 1;
+    gen = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 0;   // 0 = default choice per head dim
   }
   return gen;
 }
@@ -367,6 +377,24 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_fwd: empty problem");
   VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "vj_attn_fwd: pointers must be 16-byte aligned");
+  if (attn_fwd_generation() == 4 || attn_fwd_generation() == 0) {
+    if (HD == 128 && attn_fwd_generation() == 4)   // two CTAs per SM (S 64 + O 128 columns); opt-in until measured
+      return launch_attn_fwd4<128, 2>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+    if (HD == 32) return launch_attn_fwd4<32, 4>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+    if (HD == 64) return launch_attn_fwd4<64, 4>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+  }
+  if (attn_fwd_generation() == 5) {
+    if (HD == 32) return launch_attn_fwd4<32, 3>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+    if (HD == 64) return launch_attn_fwd4<64, 3>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+  }
+  if (attn_fwd_generation() == 3) {
+    switch (HD) {
+      case 32: return launch_attn_fwd3<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      case 64: return launch_attn_fwd3<64>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      case 128: return launch_attn_fwd3<128>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
+      default: break;
+    }
+  }
   if (attn_fwd_generation() == 2) {
     switch (HD) {
       case 32: return launch_attn_fwd2<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);

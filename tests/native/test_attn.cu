@@ -115,6 +115,8 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
       if (do_bwd) {
         // dV = P^T dO ; dP = dO V^T ; dS = P * (dP - rowsum(dO*O)) ; dQ = scale dS K ; dK = scale dS^T Q
         std::vector<double> dS((size_t)L * L);
+        static unsigned badmap[3][512];
+        memset(badmap, 0, sizeof(badmap));
         for (int i = 0; i < L; ++i) {
           double delta = 0;
           for (int d = 0; d < HD; ++d) delta += (double)dO[(size_t)(r0 + i) * D + h * HD + d] * O[(size_t)i * HD + d];
@@ -140,9 +142,23 @@ static int run(int H, int HD, int hd_real, const std::vector<int>& lens, bool do
               const double err = fabs(got - ref[w]);
               if (err > max_err_g) max_err_g = err;
               if (fabs(ref[w]) > max_g) max_g = fabs(ref[w]);
-              if (!(err <= 3e-2 + 2e-2 * fabs(ref[w]))) { if (bad < 8) printf("   grad mismatch which=%d s=%d h=%d i=%d d=%d got=%g ref=%g\n", w, s, h, i, d, got, ref[w]); ++bad; }
+              if (!(err <= 3e-2 + 2e-2 * fabs(ref[w]))) {
+                if (bad < 8) printf("   grad mismatch which=%d s=%d h=%d i=%d d=%d got=%g ref=%g\n", w, s, h, i, d, got, ref[w]);
+                ++bad;
+                if (getenv("VJ_TEST_BADMAP") && i < 512) { badmap[w][i] |= 1u << (d & 31); }
+              }
             }
           }
+        if (getenv("VJ_TEST_BADMAP")) {
+          for (int w = 0; w < 3; ++w) {
+            int nb = 0;
+            for (int i = 0; i < L && i < 512; ++i) nb += badmap[w][i] != 0;
+            if (!nb) continue;
+            printf("   badmap which=%d s=%d h=%d: %d bad rows; row:mask(d) =", w, s, h, nb);
+            for (int i = 0, k = 0; i < L && i < 512 && k < 24; ++i) if (badmap[w][i]) { printf(" %d:%08x", i, badmap[w][i]); ++k; }
+            printf("\n");
+          }
+        }
       }
     }
   }
@@ -211,6 +227,10 @@ int main(int argc, char** argv) {
     perf(16, 64, 32, 360, false);
     perf(16, 128, 24, 1568, false);
     printf("%s: %d failing case(s)\n", fails ? "FAILED" : "ALL PASSED", fails);
+    return fails ? 1 : 0;
+  }
+  if (argc > 2 && !strcmp(argv[1], "bwdone")) {   // one backward case: sequence length from the command line
+    fails += run(2, 32, 24, {atoi(argv[2])}, true);
     return fails ? 1 : 0;
   }
   if (argc > 1 && !strcmp(argv[1], "bwdbig")) {   // backward at BASELINE predictor lengths, tails, persistence

@@ -245,7 +245,13 @@ def _attention_case(dev, H, hd, lens, late_max=False, backward=True, seed=None):
         if backward:
             o.backward(do[off:off + L].double().transpose(0, 1))
             for i, t in enumerate((qq, kk, vv)):
-                close_bf16(dq_c[off:off + L, i, :, :hd], t.grad.transpose(0, 1).float(), atol=3e-2, rtol=2e-2)
+                ref_g = t.grad.transpose(0, 1).float()
+                # late_max plants keys whose probability is ~1 for ~L/7 query rows: their dK / dV rows are sums of
+                # hundreds of O(1) terms, each carrying the bf16 rounding of P and dS (2^-9 relative), so the absolute
+                # error scales with the largest gradient of the tensor rather than with the element itself
+                atol = 3e-2 + (1e-2 * float(ref_g.abs().max()) if late_max else 0.0)
+                close_bf16(dq_c[off:off + L, i, :, :hd], ref_g, atol=atol, rtol=2e-2)
+                assert rel_l2(dq_c[off:off + L, i, :, :hd], ref_g) < 1e-2
         off += L
 
 
@@ -599,10 +605,10 @@ def test_flat_grad_statistics_scaler_clip_and_loggers(dev):
     assert abs(gs.first_layer - qkv[0]) < 1e-5 * qkv[0] and abs(gs.last_layer - qkv[-1]) < 1e-5 * qkv[-1]
     # ---- clip_grad_norm_ on the device == torch's
     ref_grads = [p.grad.clone() for p in pred.parameters() if p.grad is not None]
-    total_ref = torch.nn.utils.clip_grad_norm_([torch.nn.Parameter(g.clone()) for g in ref_grads], 1e9)   # norm only
     refp = [torch.nn.Parameter(torch.zeros_like(g)) for g in ref_grads]
     for q, g in zip(refp, ref_grads):
         q.grad = g.clone()
+    total_ref = torch.nn.utils.clip_grad_norm_(refp, 1e9)   # norm only: nothing is clipped at this bound
     max_norm = float(total_ref) * 0.5
     torch.nn.utils.clip_grad_norm_(refp, max_norm)
     total = vj.clip_grad_norm_(pred, max_norm)
