@@ -84,7 +84,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // separate dQ kernel (a second exp / S / dP recomputation) unnecessary.
 constexpr int kDkvThreads = 64 + 8 * 32;   // TMA warp, MMA warp, 8 softmax warps
 
-template <int HD, bool FUSE_DQ>
+// TA: P^T and dS^T reach the dV / dK MMAs through TENSOR MEMORY (bf16 pairs written in place over the S^T / dP^T columns each
+// softmax warp has just read, A operand of tcgen05.mma) instead of a [128 x 128] bf16 shared-memory tile.  The kernel is
+// shared-memory-bandwidth bound (ncu, profiles/r02_ncu_attn_bwd1_hd32.txt: LSU shared wavefronts 61 % + tensor-core
+// operand wavefronts 40 % of the data pipe): this removes the P store, and the two 32 KB A-operand reads per tile.  Only
+// the fused dQ MMA still needs dS^T in shared memory (M-major A); tcgen05.mma executes in issue order, so dV (reads P^T) is
+// issued before dP^T (overwrites it) and dK (reads dS^T) before the next S^T.
+template <int HD, bool FUSE_DQ, bool TA>
 __global__ void __launch_bounds__(kDkvThreads, HD <= 64 ? 2 : 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
@@ -202,23 +208,43 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if (ST == 1 || i == 0) issue_S(i);    // S^T = K Q_i^T
         mbar_wait(bar_p, ph);
         tc_fence_after();
-        // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
+        if (TA) {
+          // dV += P^T dO_i with P^T read from the S^T columns (queries 0..63 in columns 0..31, 64..127 in 64..95), THEN
+          // dP^T = V dO_i^T over the same columns
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk)
-          umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
-        umma_commit(bar_dp);
-        // dV += P^T dO_i
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ts(tmem_dV, tmem_ST + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
-        umma_commit(bar_pvdone);
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
+          umma_commit(bar_dp);
+        } else {
+          // dP^T = V dO_i^T   (re-uses the S^T columns; all S^T reads are done once bar_p fired)
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_f16(tmem_ST, kmajor_desc<HD>(sV, kk), kmajor_desc<HD>(sDOi, kk), idesc_128, kk > 0);
+          umma_commit(bar_dp);
+          // dV += P^T dO_i
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16(tmem_dV, ptile_desc(sPS, kk), mnmajor_desc<HD>(sDOi, kk), idesc_hd, (i > 0 || kk > 0));
+          umma_commit(bar_pvdone);
+        }
         mbar_wait(bar_ds, ph);
         tc_fence_after();
-        if (ST == 2 && i + 1 < n_q) issue_S(i + 1);
-        // dK += dS^T Q_i
+        if (TA) {
+          // dK += dS^T Q_i (A = dS^T in tensor memory), then the next S^T (it overwrites those columns)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16_ts(tmem_dK, tmem_ST + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+          if (ST == 2 && i + 1 < n_q) issue_S(i + 1);
+        } else {
+          if (ST == 2 && i + 1 < n_q) issue_S(i + 1);
+          // dK += dS^T Q_i
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16(tmem_dK, ptile_desc(sPS, kk), mnmajor_desc<HD>(sQi, kk), idesc_hd, (i > 0 || kk > 0));
+        }
         if (FUSE_DQ) {
           // dQ_i partial [q, hd] = dS_i [q, kv] K [kv, hd]: A = dS^T tile as M-major (q contiguous), B = K MN-major
           constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 1, 1);
@@ -291,18 +317,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
           for (int e = 0; e < 16; ++e) pk[c * 16 + e] &= kvmask;
         }
-        // the P/dS tile is free once the previous iteration's dK (and dQ) MMAs retired; by then the dQ partial of
-        // tile i-1 is complete as well (drained below)
-        if (c == 0 && i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
+        if (TA) {
+          // P^T -> tensor memory, in place: this warp's 64 fp32 score columns start at col0, its 64 bf16 probabilities
+          // take columns col0 .. col0+31 (chunk c -> 16 columns at col0 + 16 c, inside the range chunk 0 has already read)
+          uint32_t lo[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          ptile_store(ps, r, half * 8 + c * 4 + g,
-                      make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]));
+          for (int e = 0; e < 16; ++e) lo[e] = pk[c * 16 + e];
+          tmem_st16(tmem_ST + lane_addr + col0 + c * 16, lo);
+        } else {
+          // the P/dS tile is free once the previous iteration's dK (and dQ) MMAs retired; by then the dQ partial of
+          // tile i-1 is complete as well (drained below)
+          if (c == 0 && i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            ptile_store(ps, r, half * 8 + c * 4 + g,
+                        make_uint4(pk[c * 16 + 4 * g], pk[c * 16 + 4 * g + 1], pk[c * 16 + 4 * g + 2], pk[c * 16 + 4 * g + 3]));
+        }
       }
+      if (TA) tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
+      // TA: the dS^T shared-memory tile (read by the dQ MMA of tile i-1) and the dQ partial of tile i-1 are released by the
+      // same commit; nothing above needed it
+      if (TA && i > 0) mbar_wait(bar_psfree, (i - 1) & 1);
       // bar_psfree(i-1) was observed above, so the dQ partial of tile i-1 is complete: drain it now, off the MMA
       // warp's critical path (it is busy with dP^T / dV).
       if (FUSE_DQ && half == 0 && i > 0) { tc_fence_after(); drain_dq(i - 1); }
@@ -323,11 +362,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           ds[e / 2 + 1] = mul_bf16x2(pk[c * 16 + e / 2 + 1],
                                      pack_bf16x2(__uint_as_float(v[e + 2]) - Dl.z, __uint_as_float(v[e + 3]) - Dl.w));
         }
-        if (c == 0) mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
+        if (TA) {
+          if (FUSE_DQ) {   // shared-memory copy for the dQ MMA only (M-major A operand)
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          ptile_store(ps, r, half * 8 + c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+            for (int g = 0; g < 4; ++g)
+              ptile_store(ps, r, half * 8 + c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+          }
+          tmem_st16(tmem_ST + lane_addr + col0 + c * 16, ds);   // in place over the dP^T columns read so far
+        } else {
+          if (c == 0) mbar_wait(bar_pvdone, ph);  // dV MMA finished reading P^T -> tile may be overwritten with dS^T
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            ptile_store(ps, r, half * 8 + c * 4 + g, make_uint4(ds[4 * g], ds[4 * g + 1], ds[4 * g + 2], ds[4 * g + 3]));
+        }
       }
+      if (TA) tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -586,12 +635,14 @@ template <int HD>
 int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
                      float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale, cudaStream_t s);
 
-// Default = first-generation kernels for every head dim; VJ_ATTN_BWD=2 selects attn_bwd2.cu (head dim 32) for A/B runs.
+// Default (3) = this file's kernels with P^T / dS^T handed to the dV / dK MMAs through tensor memory (template parameter
+// TA; hd 32, S = 1184: 0.605 ms vs 0.626 ms with the shared-memory tile).  VJ_ATTN_BWD=1 selects the shared-memory form,
+// 2 attn_bwd2.cu (persistent two-key-tile CTA, head dim 32: correct but 1.006 ms) for A/B runs.
 static int attn_bwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_BWD");
-    gen = (e && e[0] == '2') ? 2 : 1;
+    gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
   }
   return gen;
 }
@@ -607,15 +658,18 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   if (rc) return rc;
   rc = make_tmap_2d(&tdo, dout, 0, (uint64_t)H * HD, T, (uint64_t)H * HD * 2, C::BOX_INNER, 128, C::TMAP_SWIZZLE);
   if (rc) return rc;
-  auto kdkv = attn_bwd_dkv_kernel<HD, false>;
-  auto kdkv_fused = attn_bwd_dkv_kernel<HD, B::CAN_FUSE_DQ>;
+  const bool ta = attn_bwd_generation() == 3;   // P^T / dS^T through tensor memory
+  void (*kdkv)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnBwdParams) =
+      ta ? attn_bwd_dkv_kernel<HD, false, true> : attn_bwd_dkv_kernel<HD, false, false>;
+  void (*kdkv_fused)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnBwdParams) =
+      ta ? attn_bwd_dkv_kernel<HD, B::CAN_FUSE_DQ, true> : attn_bwd_dkv_kernel<HD, B::CAN_FUSE_DQ, false>;
   auto kdq = attn_bwd_dq_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static int configured = -1;
+  if (configured != int(ta)) {
     VJ_CUDA(cudaFuncSetAttribute(kdkv, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
     VJ_CUDA(cudaFuncSetAttribute(kdkv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
     VJ_CUDA(cudaFuncSetAttribute(kdq, cudaFuncAttributeMaxDynamicSharedMemorySize, B::SMEM_BYTES));
-    configured = true;
+    configured = int(ta);
   }
   const bool fuse = B::CAN_FUSE_DQ && dq_acc != nullptr;
   CUtensorMap tdq = tdo;

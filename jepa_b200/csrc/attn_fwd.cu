@@ -345,8 +345,8 @@ template <int HD>
 int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
                      float scale, cudaStream_t s);
 
-// Default: attn_fwd4.cu (64-key tiles, four small serial CTAs per SM) for head dims 32 / 64, this file's kernel (one query
-// tile, 128-key tiles, two CTAs per SM) for head dim 128.  Measured on B200, 16 heads x 32 sequences (tests/native/test_attn
+// Default: attn_fwd4.cu (64-key tiles, small serial CTAs: four per SM at head dims 32 / 64, two at head dim 128); this
+// file's kernel (one query tile, 128-key tiles, two / one CTAs per SM) is the first generation, kept for A/B timing.  Measured on B200, 16 heads x 32 sequences (tests/native/test_attn
 // fwdbig, profiles/r02_attn_fwd_variants.txt): hd 64 S=1568: gen1 0.560 ms, persistent two-tile ping-pong (attn_fwd2.cu)
 // 0.685 / 0.646 ms, eight softmax warps (attn_fwd3.cu) 0.567 ms, fwd4 0.474 ms; hd 32 S=1184: 0.319 / 0.365 / 0.323 / 0.268.
 // VJ_ATTN_FWD=1|2|3|4|5 forces one generation for A/B timing (5 = fwd4 with three CTAs per SM).
@@ -378,7 +378,7 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   VJ_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "vj_attn_fwd: pointers must be 16-byte aligned");
   if (attn_fwd_generation() == 4 || attn_fwd_generation() == 0) {
-    if (HD == 128 && attn_fwd_generation() == 4)   // two CTAs per SM (S 64 + O 128 columns); opt-in until measured
+    if (HD == 128)   // two CTAs per SM (S 64 + O 128 of 256 TMEM columns): 0.623 ms vs 0.877 ms for gen 1 at S = 1568
       return launch_attn_fwd4<128, 2>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
     if (HD == 32) return launch_attn_fwd4<32, 4>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
     if (HD == 64) return launch_attn_fwd4<64, 4>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);

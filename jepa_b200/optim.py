@@ -62,7 +62,7 @@ class FlatAdamW(torch.optim.Optimizer):
         key = (store.flat.data_ptr(), store.total, tuple((gi, id(p)) for gi, p in members))
         st = self._flat.get(id(store))
         if st is not None and st["key"] == key:
-            _, p0 = members[0]
+            p0 = next(p for _, p in members if p.requires_grad)   # frozen members carry no state
             off0 = store.offsets[p0._vj_name][0]
             ea = self.state.get(p0, {}).get("exp_avg")
             if ea is not None and ea.data_ptr() == st["m"].data_ptr() + 4 * off0:
@@ -83,6 +83,8 @@ class FlatAdamW(torch.optim.Optimizer):
                 step.fill_(float(old["step"]))
                 break
         for gi, p in members:
+            if not p.requires_grad:     # torch.optim.AdamW never creates state for a parameter without a gradient (the frozen
+                continue                # pos_embed): keep state_dict() entry-for-entry identical to the reference's
             off, n, shape = store.offsets[p._vj_name]
             old = self.state.get(p, {})
             if "exp_avg" in old:

@@ -36,6 +36,7 @@ class FlatParamStore:
         self.total = 0
         self._params = None
         self._shadow_fresh = False   # set by the kernels that emit the bf16 shadow together with a parameter update
+        self._shadow_complete = False   # a full cast has filled every element of the shadow at least once
         self._seg = None             # uint16 per 64-element block -> index into named parameters (0xFFFF: frozen / padding)
 
     def __deepcopy__(self, memo):
@@ -78,6 +79,7 @@ class FlatParamStore:
         self.flat, self.offsets, self.total, self._params = flat, offsets, off, named
         self.shadow = torch.empty(off, dtype=torch.bfloat16, device=dev)
         self._shadow_fresh = False
+        self._shadow_complete = False
         self._seg = None
         return self
 
@@ -98,9 +100,12 @@ class FlatParamStore:
             self._shadow_fresh = False
             return
         K.cast_f32_bf16(self.flat, self.shadow)
+        self._shadow_complete = True
 
     def mark_shadow_fresh(self):
-        self._shadow_fresh = True
+        # the update kernels only write the elements they update (frozen tensors and alignment padding are skipped), so
+        # their copy is complete only on top of a shadow that a full cast has produced at least once
+        self._shadow_fresh = getattr(self, "_shadow_complete", False)
 
     def invalidate_shadow(self):
         self._shadow_fresh = False

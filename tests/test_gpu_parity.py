@@ -249,9 +249,9 @@ def _attention_case(dev, H, hd, lens, late_max=False, backward=True, seed=None):
                 # late_max plants keys whose probability is ~1 for ~L/7 query rows: their dK / dV rows are sums of
                 # hundreds of O(1) terms, each carrying the bf16 rounding of P and dS (2^-9 relative), so the absolute
                 # error scales with the largest gradient of the tensor rather than with the element itself
-                atol = 3e-2 + (1e-2 * float(ref_g.abs().max()) if late_max else 0.0)
+                atol = 3e-2 + (2e-2 * float(ref_g.abs().max()) if late_max else 0.0)
                 close_bf16(dq_c[off:off + L, i, :, :hd], ref_g, atol=atol, rtol=2e-2)
-                assert rel_l2(dq_c[off:off + L, i, :, :hd], ref_g) < 1e-2
+                assert rel_l2(dq_c[off:off + L, i, :, :hd], ref_g) < (2e-2 if late_max else 1e-2)   # stated gradient tolerance: 3e-2
         off += L
 
 
@@ -414,7 +414,8 @@ def test_wgrad_split_k_full_token_counts(dev, T, n_out, k_in):
     got = dw[r0:r0 + 256, c0:c0 + 256].cpu()
     e = rel_l2(got, ref)
     print(f"wgrad T={T} {n_out}x{k_in} split_k={sk}: rel-L2 vs fp64 {e:.3e}")
-    assert e < 2e-5, (sk, e)             # fp32 tensor-core accumulation over up to 76 032 products per output
+    # fp32 tensor-core accumulation over up to 76 032 products per output: summation-order noise ~ sqrt(K) * 2^-24 = 1.6e-5
+    assert e < 5e-5, (sk, e)
     # stream-K decomposition of the same GEMM (split_k = -1): identical result up to summation order
     dw2 = base.clone().to(dev)
     Kn.gemm(dy.to(dev, torch.bfloat16), x.to(dev, torch.bfloat16), dw2, a_mn=True, b_mn=True, accumulate=True, split_k=-1)
@@ -571,7 +572,7 @@ def test_flat_grad_statistics_scaler_clip_and_loggers(dev):
                                  crop_size=224, pred_depth=2, pred_embed_dim=384, uniform_power=True,
                                  use_mask_tokens=True, num_mask_tokens=2, use_sdpa=True)
     for net in (enc, pred):
-        net.backbone._store.adopt(net.backbone)
+        net.backbone._store.adopt(net.backbone).refresh_shadow()   # what every forward does first: the bf16 operands exist
     opt, scaler, sch, wds = init_opt(enc, pred, iterations_per_epoch=10, start_lr=1e-3, ref_lr=2e-3, warmup=1, num_epochs=2,
                                      wd=0.04, final_wd=0.4, mixed_precision=True)
     assert isinstance(scaler, FlatGradScaler)
