@@ -102,10 +102,12 @@ class FlatParamStore:
         K.cast_f32_bf16(self.flat, self.shadow)
         self._shadow_complete = True
 
-    def mark_shadow_fresh(self):
-        # the update kernels only write the elements they update (frozen tensors and alignment padding are skipped), so
-        # their copy is complete only on top of a shadow that a full cast has produced at least once
-        self._shadow_fresh = getattr(self, "_shadow_complete", False)
+    def mark_shadow_fresh(self, complete=False):
+        # AdamW only writes the elements it updates (frozen tensors and alignment padding are skipped), so its copy is
+        # complete only on top of a shadow a full pass (cast, or the EMA kernel: complete=True) has filled at least once
+        if complete:
+            self._shadow_complete = True
+        self._shadow_fresh = self._shadow_complete
 
     def invalidate_shadow(self):
         self._shadow_fresh = False

@@ -111,7 +111,7 @@ def ema_update(encoder, target_encoder, m):
         raise RuntimeError("encoder / target_encoder parameter layouts differ")
     # the bf16 tensor-core operands of the target's next forward leave in the same pass (no separate cast launch)
     K.ema_update_shadow(ks.flat, qs.flat, m, ks.shadow)
-    ks.mark_shadow_fresh()
+    ks.mark_shadow_fresh(complete=True)   # the EMA pass walks the WHOLE flat buffer (frozen tensors and padding included)
 
 
 @torch.no_grad()

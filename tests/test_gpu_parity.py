@@ -556,7 +556,9 @@ def test_flat_adamw_single_launch_matches_torch(dev):
         assert rel_l2(p.detach().cpu(), c.detach().cpu()) < 2e-6
     assert torch.equal(enc.backbone.pos_embed.detach(), pos0)
     sd = opt.state_dict()
-    assert len(sd["state"]) == len(ref_params) and float(next(iter(sd["state"].values()))["step"]) == 3.0
+    # entry for entry what torch.optim.AdamW keeps: no state for the frozen pos_embed tensors (they never get a gradient)
+    assert len(sd["state"]) == len(ref.state_dict()["state"]) == len(ref_params) - 2
+    assert float(next(iter(sd["state"].values()))["step"]) == 3.0
 
 
 def test_flat_grad_statistics_scaler_clip_and_loggers(dev):

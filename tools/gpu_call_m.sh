@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2 GPU session M: backward half-chains (VJ_ATTN_BWD=4) vs TA (3); full pytest on the default path; step launch list.
+mkdir -p gpurun_out
+O=gpurun_out
+( cd tests/native
+  export VJ_TEST_BADMAP=1
+  VJ_ATTN_BWD=4 timeout 200 ./test_attn > ../../$O/r02_m_attn_bwd4_small.log 2>&1
+  VJ_ATTN_BWD=4 timeout 300 ./test_attn bwdbig > ../../$O/r02_m_attn_bwd4_big.log 2>&1
+  VJ_ATTN_BWD=3 timeout 300 ./test_attn bwdbig > ../../$O/r02_m_attn_bwd3_big.log 2>&1 )
+grep -E "PERF|FAIL|PASSED|badmap" $O/r02_m_attn_bwd4_small.log | cut -c1-250 | tail -8
+grep -E "PERF|FAIL|PASSED|badmap" $O/r02_m_attn_bwd4_big.log | cut -c1-250 | tail -10
+grep -E "PERF|FAIL|PASSED" $O/r02_m_attn_bwd3_big.log | tail -4
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -rA > $O/r02_m_pytest.log 2>&1
+tail -5 $O/r02_m_pytest.log
+timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> $O/r02_m_bench.err | grep '^{"metric' > $O/r02_m_bench.json
+VJ_ATTN_BWD=4 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> $O/r02_m_bench_bwd4.err | grep '^{"metric' > $O/r02_m_bench_bwd4.json
+head -c 260 $O/r02_m_bench.json; echo; head -c 260 $O/r02_m_bench_bwd4.json; echo
+( cd tests/native; VJ_ATTN_BWD=4 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_dkv --launch-skip 8 -c 1 -o ../../$O/r02_prof_attn_bwd4_hd32 ./test_attn perf > ../../$O/r02_m_ncu_bwd4.log 2>&1 )
