@@ -240,8 +240,10 @@ def ddp_gradient_check(st, clips, masks_enc, masks_pred):
 def ncu_gemm_traffic(cfg_name):
     """DRAM bytes moved by the GEMM family in one step, from the committed ncu launch list of `bench.py --profile`
     (profiles/, vitl16 only); None when no capture exists for this config."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_step_launches_final_summary.txt")
-    if cfg_name != "vitl16" or not os.path.exists(path):
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    path = next((p for p in (os.path.join(prof, "r02_step_launches_summary.txt"),
+                             os.path.join(prof, "r01_step_launches_final_summary.txt")) if os.path.exists(p)), "")
+    if cfg_name != "vitl16" or not path:
         return None
     with open(path) as f:
         for line in f:

@@ -630,19 +630,16 @@ int launch_attn_dq_convert(const float* dq_acc, void* dqkv, long long T, int HHD
   return 0;
 }
 
-// second-generation fused backward for head dims <= 32 (attn_bwd2.cu)
-template <int HD>
-int launch_attn_bwd2(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
-                     float* dq_acc, const int* cu, int nseq, int max_len, int H, int T, float scale, cudaStream_t s);
-
 // Default (3) = this file's kernels with P^T / dS^T handed to the dV / dK MMAs through tensor memory (template parameter
-// TA; hd 32, S = 1184: 0.605 ms vs 0.626 ms with the shared-memory tile).  VJ_ATTN_BWD=1 selects the shared-memory form,
-// 2 attn_bwd2.cu (persistent two-key-tile CTA, head dim 32: correct but 1.006 ms) for A/B runs.
+// TA; hd 32, S = 1184: 0.605 ms vs 0.626 ms with the shared-memory tile).  VJ_ATTN_BWD=1 selects the shared-memory form for
+// A/B runs.  Built, validated, measured and removed again in round 2 (git history): attn_bwd2.cu, a persistent CTA owning two
+// key tiles with ping-pong softmax groups (1.006 ms), and a "half chain" variant of this kernel whose two 64-query halves had
+// their own barriers and a polling MMA thread (0.663 ms).
 static int attn_bwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_BWD");
-    gen = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
+    gen = (e && e[0] == '1') ? 1 : 3;
   }
   return gen;
 }
@@ -720,8 +717,6 @@ extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, c
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
   VJ_CHECK_ARG(qkv && out && dout && lse2 && delta_ws && dqkv && cu_seqlens, "vj_attn_bwd: null pointer");
   VJ_CHECK_ARG(nseq > 0 && max_len > 0 && H > 0 && T > 0, "vj_attn_bwd: empty problem");
-  if (HD == 32 && dq_acc_ws != nullptr && attn_bwd_generation() == 2)
-    return launch_attn_bwd2<32>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
   switch (HD) {
     case 32: return launch_attn_bwd<32>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);
     case 64: return launch_attn_bwd<64>(qkv, out, dout, lse2, delta_ws, dqkv, dq_acc_ws, cu_seqlens, nseq, max_len, H, T, scale, s);

@@ -340,21 +340,14 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   return 0;
 }
 
-// second-generation kernel (attn_fwd2.cu): persistent, two query tiles per CTA, ping-pong softmax groups
-template <int HD>
-int launch_attn_fwd2(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
-                     float scale, cudaStream_t s);
-
-// Default: attn_fwd4.cu (64-key tiles, small serial CTAs: four per SM at head dims 32 / 64, two at head dim 128); this
-// file's kernel (one query tile, 128-key tiles, two / one CTAs per SM) is the first generation, kept for A/B timing.  Measured on B200, 16 heads x 32 sequences (tests/native/test_attn
-// fwdbig, profiles/r02_attn_fwd_variants.txt): hd 64 S=1568: gen1 0.560 ms, persistent two-tile ping-pong (attn_fwd2.cu)
-// 0.685 / 0.646 ms, eight softmax warps (attn_fwd3.cu) 0.567 ms, fwd4 0.474 ms; hd 32 S=1184: 0.319 / 0.365 / 0.323 / 0.268.
-// VJ_ATTN_FWD=1|2|3|4|5 forces one generation for A/B timing (5 = fwd4 with three CTAs per SM).
-// VJ_ATTN_FWD=3 selects attn_fwd3.cu (gen-1 CTA with eight softmax warps, two threads per query row).
-template <int HD>
-int launch_attn_fwd3(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
-                     float scale, cudaStream_t s);
-// VJ_ATTN_FWD=4 / 5 select attn_fwd4.cu (64-key tiles, fully serial CTAs, four / three of them per SM; head dims 32, 64).
+// Default: attn_fwd4.cu (64-key tiles, small serial CTAs: four per SM at head dims 32 / 64, two at head dim 128).  This
+// file's kernel (one query tile per CTA, 128-key tiles, two / one CTAs per SM) is the first generation, kept for A/B
+// timing: VJ_ATTN_FWD=1 selects it, 4 forces fwd4, 5 = fwd4 with three CTAs per SM.
+// Measured on B200, 16 heads x 32 sequences (tests/native/test_attn fwdbig, profiles/r02_attn_fwd_variants.txt):
+//   hd 64, S = 1568: this kernel 0.560 ms, fwd4 0.474 ms;  hd 32, S = 1184: 0.319 / 0.268 ms;  hd 128: 0.877 / 0.623 ms.
+// Two more organisations were built, validated and measured in round 2 and then removed from the tree (git history):
+// attn_fwd2.cu, a persistent CTA with two query tiles and ping-pong softmax groups (0.685 ms, 0.646 ms free-running), and
+// attn_fwd3.cu, this kernel with eight softmax warps, two threads per query row (0.567 ms).
 template <int HD, int NCTA>
 int launch_attn_fwd4(const void* qkv, void* out, float* lse2, const int* cu, int nseq, int max_len, int H, int T,
                      float scale, cudaStream_t s);
@@ -362,7 +355,7 @@ static int attn_fwd_generation() {
   static int gen = -1;
   if (gen < 0) {
     const char* e = getenv("VJ_ATTN_FWD");
-    gen = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 0;   // 0 = default choice per head dim
+    gen = (e && (e[0] == '1' || e[0] == '4' || e[0] == '5')) ? e[0] - '0' : 0;   // 0 = default choice per head dim
   }
   return gen;
 }
@@ -386,22 +379,6 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse2, const int* c
   if (attn_fwd_generation() == 5) {
     if (HD == 32) return launch_attn_fwd4<32, 3>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
     if (HD == 64) return launch_attn_fwd4<64, 3>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-  }
-  if (attn_fwd_generation() == 3) {
-    switch (HD) {
-      case 32: return launch_attn_fwd3<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      case 64: return launch_attn_fwd3<64>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      case 128: return launch_attn_fwd3<128>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      default: break;
-    }
-  }
-  if (attn_fwd_generation() == 2) {
-    switch (HD) {
-      case 32: return launch_attn_fwd2<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      case 64: return launch_attn_fwd2<64>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      case 128: return launch_attn_fwd2<128>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
-      default: break;
-    }
   }
   switch (HD) {
     case 32: return launch_attn_fwd<32>(qkv, out, lse2, cu_seqlens, nseq, max_len, H, T, scale, s);
