@@ -107,9 +107,6 @@ def main(args, resume_preempt=False):
     loss_cfg = args.get('loss')
     loss_exp = loss_cfg.get('loss_exp')
     reg_coeff = loss_cfg.get('reg_coeff')
-    if reg_coeff != 0.0:
-        raise NotImplementedError("reg_coeff != 0: the variance regulariser is computed for logging only "
-                                  "(its gradient is not implemented; every shipped config uses 0.0)")
 
     opt_cfg = args.get('optimization')
     ipe = opt_cfg.get('ipe', None)
@@ -289,7 +286,7 @@ def main(args, resume_preempt=False):
                 z = encoder(clips, masks_enc)
                 z = predictor(z, h, masks_enc, masks_pred)
                 loss_jepa = vj.jepa_loss(z, h, loss_exp)
-                loss_reg = vj.reg_loss(z)
+                loss_reg = vj.reg_loss(z, with_grad=(reg_coeff != 0.0))   # differentiable only when it is used
                 loss = loss_jepa + reg_coeff * loss_reg
 
                 # Step 2. backward & optimizer step (GradScaler kept: it is active for bf16 in the reference too)

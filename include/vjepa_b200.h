@@ -129,6 +129,15 @@ int vj_l1_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, 
 /* dz bf16 = sign(z - h) * scale * (grad_scale_dev ? *grad_scale_dev : 1). */
 int vj_l1_loss_bwd(const void* z, const float* h, const float* grad_scale_dev, float scale, void* dz,
                    long long n, void* stream);
+/* General exponent of loss_fn (app/vjepa/train.py:440-446, loss_exp != 1): *loss_sum += weight * sum |z - h|^p;
+ * dz bf16 = sign(z - h) |z - h|^(p-1) * scale * (grad_scale_dev ? *grad_scale_dev : 1). */
+int vj_lp_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, float weight, float p, void* stream);
+int vj_lp_loss_bwd(const void* z, const float* h, const float* grad_scale_dev, float scale, void* dz, long long n, float p,
+                   void* stream);
+/* Backward of the variance regulariser (reg_fn + relu-mean, app/vjepa/train.py:448-449,458-459, reg_coeff != 0) for one
+ * mask: dz[b,k,d] = -[pstd_total[b,d] < 1] / (B D) * weight * (z - mean_k z) / ((K-1) sqrt(var_k + eps)) * scale * *grad_scale_dev. */
+int vj_token_std_bwd(const void* z, const float* pstd_total, const float* grad_scale_dev, float scale, void* dz, int B, int K,
+                     int D, float eps, float weight, void* stream);
 /* pstd[b,d] += weight * sqrt(var_unbiased_k(z[b,k,d]) + eps).  reg_fn, app/vjepa/train.py:448-449. */
 int vj_token_std_accum(const void* z, float* pstd, int B, int K, int D, float eps, float weight, void* stream);
 

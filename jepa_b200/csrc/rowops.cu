@@ -367,6 +367,76 @@ __global__ void __launch_bounds__(256) l1_loss_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// General exponent p of loss_fn (train.py:440-446): sum |z - h|^p * weight (weight carries 1 / (M n p)); p = 1 has its own
+// kernels above.
+__global__ void __launch_bounds__(256) lp_loss_fwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ h,
+                                                          float* __restrict__ loss_sum, long long n8, float weight, float p) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8<false>(z, i * 8, a);
+    load8<true>(h, i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = fabsf(a[j] - b[j]);
+      acc += d > 0.f ? powf(d, p) : 0.f;
+    }
+  }
+  __shared__ float sm[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sm[w];
+    atomicAdd(loss_sum, s * weight);
+  }
+}
+// dz = sign(d) |d|^(p-1) * scale * (*gscale)   (the 1/p of the loss cancels the p of the derivative)
+__global__ void __launch_bounds__(256) lp_loss_bwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ h,
+                                                          const float* __restrict__ gscale, float scale,
+                                                          __nv_bfloat16* __restrict__ dz, long long n8, float p) {
+  const float sc = scale * (gscale ? *gscale : 1.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8], o[8];
+    load8<false>(z, i * 8, a);
+    load8<true>(h, i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = a[j] - b[j];
+      const float m = fabsf(d);
+      o[j] = m > 0.f ? copysignf(sc * powf(m, p - 1.0f), d) : 0.f;
+    }
+    store8<false>(dz, i * 8, o);
+  }
+}
+
+// Backward of the variance regulariser (train.py:448-449,458-459) for one mask:
+//   loss_reg = mean_{b,d} relu(1 - pstd[b,d]),  pstd = sum_i w * sqrt(var_unbiased_k(z_i[b,k,d]) + eps)
+//   d loss_reg / d z_i[b,k,d] = -[pstd < 1] / (B D) * w * (z - mean_k z) / ((K - 1) * sqrt(var + eps))
+__global__ void __launch_bounds__(128) token_std_bwd_kernel(const __nv_bfloat16* __restrict__ z,
+                                                            const float* __restrict__ pstd_total,
+                                                            const float* __restrict__ gscale, float scale,
+                                                            __nv_bfloat16* __restrict__ dz, int B, int K, int D, float eps,
+                                                            float weight) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (d >= D) return;
+  const __nv_bfloat16* p = z + (long long)b * K * D + d;
+  __nv_bfloat16* q = dz + (long long)b * K * D + d;
+  float s = 0.f, ss = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float v = __bfloat162float(p[(long long)k * D]);
+    s += v;
+    ss += v * v;
+  }
+  const float mean = s / K;
+  const float var = fmaxf((ss - K * mean * mean) / (K - 1), 0.f);
+  const float g = scale * (gscale ? *gscale : 1.0f);
+  const float c = pstd_total[(long long)b * D + d] < 1.0f ? -g * weight / ((float)B * D * (K - 1) * sqrtf(var + eps)) : 0.f;
+  for (int k = 0; k < K; ++k) q[(long long)k * D] = __float2bfloat16(c * (__bfloat162float(p[(long long)k * D]) - mean));
+}
+
 // Per-(b, d) unbiased variance of z over the token dim -> pstd = sqrt(var + 1e-4)  (train.py:448-449)
 __global__ void __launch_bounds__(256) token_std_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ pstd,
                                                         int B, int K, int D, float eps, float weight) {
@@ -551,6 +621,47 @@ extern "C" int vj_l1_loss_bwd(const void* z, const float* h, const float* grad_s
   l1_loss_bwd_kernel<<<grid_for(n / 8, 256 * 4), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), h,
                                                               grad_scale_dev, scale,
                                                               reinterpret_cast<__nv_bfloat16*>(dz), n / 8);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}
+
+extern "C" int vj_lp_loss_fwd(const void* z, const float* h, float* loss_sum, long long n, float weight, float p,
+                              void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(z && h && loss_sum, "vj_lp_loss_fwd: null pointer");
+  VJ_CHECK_ARG(n % 8 == 0 && p > 0.f, "vj_lp_loss_fwd: n must be a multiple of 8 and the exponent positive");
+  if (n <= 0) return 0;
+  lp_loss_fwd_kernel<<<grid_for(n / 8, 256 * 4), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), h, loss_sum,
+                                                              n / 8, weight, p);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}
+
+extern "C" int vj_lp_loss_bwd(const void* z, const float* h, const float* grad_scale_dev, float scale, void* dz,
+                              long long n, float p, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(z && h && dz, "vj_lp_loss_bwd: null pointer");
+  VJ_CHECK_ARG(n % 8 == 0 && p >= 1.f, "vj_lp_loss_bwd: n must be a multiple of 8 and the exponent >= 1");
+  if (n <= 0) return 0;
+  lp_loss_bwd_kernel<<<grid_for(n / 8, 256 * 4), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), h,
+                                                              grad_scale_dev, scale,
+                                                              reinterpret_cast<__nv_bfloat16*>(dz), n / 8, p);
+  VJ_CUDA(cudaGetLastError());
+  vj::count_launch(1);
+  return 0;
+}
+
+extern "C" int vj_token_std_bwd(const void* z, const float* pstd_total, const float* grad_scale_dev, float scale, void* dz,
+                                int B, int K, int D, float eps, float weight, void* stream_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK_ARG(z && pstd_total && dz, "vj_token_std_bwd: null pointer");
+  VJ_CHECK_ARG(K > 1, "vj_token_std_bwd: needs K > 1");
+  if (B <= 0) return 0;
+  dim3 grid((D + 127) / 128, B);
+  token_std_bwd_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(z), pstd_total, grad_scale_dev, scale,
+                                            reinterpret_cast<__nv_bfloat16*>(dz), B, K, D, eps, weight);
   VJ_CUDA(cudaGetLastError());
   vj::count_launch(1);
   return 0;

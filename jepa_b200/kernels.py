@@ -189,6 +189,25 @@ def l1_loss_bwd(z, h, grad_scale, scale, dz):
     return dz
 
 
+def lp_loss_fwd(z, h, loss_sum, weight, p):
+    _chk(z, BF16, "z"); _chk(h, F32, "h"); _chk(loss_sum, F32, "loss_sum")
+    _lib.call("vj_lp_loss_fwd", _p(z), _p(h), _p(loss_sum), z.numel(), float(weight), float(p), _s())
+
+
+def lp_loss_bwd(z, h, grad_scale, scale, dz, p):
+    _chk(z, BF16, "z"); _chk(h, F32, "h"); _chk(dz, BF16, "dz")
+    _lib.call("vj_lp_loss_bwd", _p(z), _p(h), _p(grad_scale), float(scale), _p(dz), z.numel(), float(p), _s())
+    return dz
+
+
+def token_std_bwd(z, pstd_total, grad_scale, scale, dz, weight, eps=1e-4):
+    _chk(z, BF16, "z"); _chk(pstd_total, F32, "pstd_total"); _chk(dz, BF16, "dz")
+    B, K, D = z.shape
+    _lib.call("vj_token_std_bwd", _p(z), _p(pstd_total), _p(grad_scale), float(scale), _p(dz), B, K, D, float(eps),
+              float(weight), _s())
+    return dz
+
+
 def token_std_accum(z, pstd, weight, eps=1e-4):
     _chk(z, BF16, "z"); _chk(pstd, F32, "pstd")
     B, K, D = z.shape

@@ -48,18 +48,24 @@ def forward_target(target_encoder, clips, masks_pred):
     return _token_views(h_cat, B, sizes)
 
 
-class _L1LossFn(torch.autograd.Function):
+class _LpLossFn(torch.autograd.Function):
+    """(1/M) sum_i mean(|z_i - h_i|^p) / p over the concatenated token rows of all masks; p = 1 takes the L1 kernels."""
+
     @staticmethod
-    def forward(ctx, z_cat, h_cat, row_counts):
+    def forward(ctx, z_cat, h_cat, row_counts, p):
         n_masks = len(row_counts)
         D = z_cat.shape[1]
         loss = torch.zeros(1, dtype=torch.float32, device=z_cat.device)
         off = 0
         for rows in row_counts:
-            K.l1_loss_fwd(z_cat[off:off + rows], h_cat[off:off + rows], loss, 1.0 / (n_masks * rows * D))
+            w = 1.0 / (n_masks * rows * D)
+            if p == 1.0:
+                K.l1_loss_fwd(z_cat[off:off + rows], h_cat[off:off + rows], loss, w)
+            else:
+                K.lp_loss_fwd(z_cat[off:off + rows], h_cat[off:off + rows], loss, w / p, p)
             off += rows
         ctx.save_for_backward(z_cat, h_cat)
-        ctx.row_counts = row_counts
+        ctx.row_counts, ctx.p = row_counts, p
         return loss.view(())
 
     @staticmethod
@@ -71,35 +77,71 @@ class _L1LossFn(torch.autograd.Function):
         dz = torch.empty_like(z_cat)
         off = 0
         for rows in ctx.row_counts:
-            K.l1_loss_bwd(z_cat[off:off + rows], h_cat[off:off + rows], g, 1.0 / (n_masks * rows * D),
-                          dz[off:off + rows])
+            w = 1.0 / (n_masks * rows * D)
+            if ctx.p == 1.0:
+                K.l1_loss_bwd(z_cat[off:off + rows], h_cat[off:off + rows], g, w, dz[off:off + rows])
+            else:
+                K.lp_loss_bwd(z_cat[off:off + rows], h_cat[off:off + rows], g, w, dz[off:off + rows], ctx.p)
             off += rows
-        return dz, None, None
+        return dz, None, None, None
+
+
+def _cat_rows(views, dtype):
+    base = _common_base(views)
+    if base is None:
+        base = torch.cat([t.reshape(-1, t.shape[-1]) for t in views], dim=0)
+    return base if base.dtype == dtype else base.to(dtype)
 
 
 def jepa_loss(z, h, loss_exp=1.0):
-    """loss_fn (train.py:440-446): (1/M) sum_i mean(|z_i - h_i|^p) / p, fused for p = 1."""
-    if loss_exp != 1.0:
-        raise NotImplementedError("only loss_exp=1.0 (L1, every shipped config) is implemented on the accelerated path")
-    zb, hb = _common_base(z), _common_base(h)
-    if zb is None:
-        zb = torch.cat([t.reshape(-1, t.shape[-1]) for t in z], dim=0)
-    if hb is None:
-        hb = torch.cat([t.reshape(-1, t.shape[-1]) for t in h], dim=0)
-    if zb.dtype != torch.bfloat16:
-        zb = zb.to(torch.bfloat16)
+    """loss_fn (train.py:440-446): (1/M) sum_i mean(|z_i - h_i|^p) / p; p = loss_exp (1.0 in every shipped config)."""
+    p = float(loss_exp)
+    if not p >= 1.0:
+        raise ValueError(f"loss_exp must be >= 1 (got {loss_exp}): |z - h|^p has no finite gradient at z = h otherwise")
+    zb, hb = _cat_rows(z, torch.bfloat16), _cat_rows(h, torch.float32)
     rows = tuple(int(t.shape[0] * t.shape[1]) for t in z)
-    return _L1LossFn.apply(zb.contiguous(), hb.float().contiguous(), rows)
+    return _LpLossFn.apply(zb.contiguous(), hb.contiguous(), rows, p)
 
 
-@torch.no_grad()
-def reg_loss(z):
-    """reg_fn + relu-mean (train.py:448-449,458-459); value is only logged (reg_coeff = 0 in all configs)."""
-    B, _, D = z[0].shape
-    pstd = torch.zeros(B, D, dtype=torch.float32, device=z[0].device)
-    for zi in z:
-        K.token_std_accum(zi.detach().contiguous(), pstd, 1.0 / len(z))
-    return torch.mean(F.relu(1. - pstd))
+class _RegLossFn(torch.autograd.Function):
+    """reg_fn + relu-mean (train.py:448-449,458-459): mean(relu(1 - (1/M) sum_i sqrt(var_unbiased(z_i, dim=1) + 1e-4)))."""
+
+    @staticmethod
+    def forward(ctx, z_cat, B, sizes):
+        D = z_cat.shape[1]
+        pstd = torch.zeros(B, D, dtype=torch.float32, device=z_cat.device)
+        off = 0
+        for k in sizes:
+            K.token_std_accum(z_cat[off:off + B * k].view(B, k, D), pstd, 1.0 / len(sizes))
+            off += B * k
+        ctx.save_for_backward(z_cat, pstd)
+        ctx.B, ctx.sizes = B, sizes
+        return torch.mean(F.relu(1. - pstd))          # [B, D] epilogue of the regulariser (the kernels did the token reduction)
+
+    @staticmethod
+    def backward(ctx, g):
+        z_cat, pstd = ctx.saved_tensors
+        B, sizes, D = ctx.B, ctx.sizes, z_cat.shape[1]
+        g = g.detach().to(torch.float32).reshape(1).contiguous()
+        dz = torch.empty_like(z_cat)
+        off = 0
+        for k in sizes:
+            K.token_std_bwd(z_cat[off:off + B * k].view(B, k, D), pstd, g, 1.0, dz[off:off + B * k].view(B, k, D),
+                            1.0 / len(sizes))
+            off += B * k
+        return dz, None, None
+
+
+def reg_loss(z, with_grad=False):
+    """reg_fn + relu-mean (train.py:448-449,458-459).  with_grad=False (reg_coeff = 0, every shipped config): the value is
+    only logged; with_grad=True: differentiable through the hand-written backward kernel (reg_coeff != 0)."""
+    B = int(z[0].shape[0])
+    sizes = tuple(int(t.shape[1]) for t in z)
+    zb = _cat_rows(z, torch.bfloat16).contiguous()
+    if with_grad and zb.requires_grad:
+        return _RegLossFn.apply(zb, B, sizes)
+    with torch.no_grad():
+        return _RegLossFn.apply(zb.detach(), B, sizes)
 
 
 @torch.no_grad()

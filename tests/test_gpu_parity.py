@@ -307,6 +307,38 @@ def test_target_ln_gather_and_loss(dev):
     assert abs(float(vj.reg_loss([t.to(dev, torch.bfloat16) for t in z])) - float(O.reg_fn(z))) < 1e-4
 
 
+@pytest.mark.parametrize("loss_exp,reg_coeff", [(2.0, 0.0), (1.5, 0.0), (1.0, 0.7), (2.0, 0.3)])
+def test_loss_exponent_and_variance_regulariser_gradients(dev, loss_exp, reg_coeff):
+    """loss_fn with loss_exp != 1 and the reg_fn term with reg_coeff != 0 (app/vjepa/train.py:440-449,456-459): value and
+    d loss / d z of the hand-written kernels vs autograd over the oracle's restatement."""
+    from jepa_b200 import step as vj
+    from jepa_b200.models import _token_views
+    from oracle import vjepa_oracle as O
+    B, D, sizes = 3, 192, [40, 24]
+    g = torch.Generator().manual_seed(int(loss_exp * 10 + reg_coeff * 100))
+    # token spread below AND above 1 so that relu(1 - pstd) is active for some (b, d) columns and inactive for others
+    z = [bf(torch.randn(B, k, D, generator=g) * torch.linspace(0.3, 1.8, D)) for k in sizes]
+    h = [torch.randn(B, k, D, generator=g) for k in sizes]
+    zc = torch.cat([t.reshape(-1, D) for t in z]).to(dev, torch.bfloat16).requires_grad_(True)
+    hc = torch.cat([t.reshape(-1, D) for t in h]).to(dev)
+    zv, hv = _token_views(zc, B, sizes), _token_views(hc, B, sizes)
+    loss_jepa = vj.jepa_loss(zv, hv, loss_exp)
+    loss_reg = vj.reg_loss(zv, with_grad=reg_coeff != 0.0)
+    loss = loss_jepa + reg_coeff * loss_reg
+    (loss * 1024.0).backward()
+    zr = [t.clone().requires_grad_(True) for t in z]
+    lj, lr_ = O.loss_fn(zr, h, loss_exp), O.reg_fn(zr)
+    ((lj + reg_coeff * lr_) * 1024.0).backward()
+    assert abs(float(loss_jepa) - float(lj)) < 2e-5 * max(1.0, abs(float(lj)))
+    assert abs(float(loss_reg) - float(lr_)) < 2e-5
+    ref = torch.cat([t.grad.reshape(-1, D) for t in zr])
+    assert float(ref.abs().max()) > 0
+    assert rel_l2(zc.grad.float().cpu(), ref) < 6e-3          # dz is stored in bf16 (2^-9 per element)
+    # the no-grad (logging-only) form returns the same value and leaves no graph
+    with torch.no_grad():
+        assert abs(float(vj.reg_loss(zv)) - float(lr_)) < 2e-5
+
+
 def test_ema_bit_exact_and_adamw(dev):
     from jepa_b200 import kernels as Kn
     from jepa_b200.optim import FlatAdamW
