@@ -141,6 +141,14 @@ int vj_token_std_bwd(const void* z, const float* pstd_total, const float* grad_s
 /* pstd[b,d] += weight * sqrt(var_unbiased_k(z[b,k,d]) + eps).  reg_fn, app/vjepa/train.py:448-449. */
 int vj_token_std_accum(const void* z, float* pstd, int B, int K, int D, float eps, float weight, void* stream);
 
+/* ---- attentive probe (frozen-encoder evaluation) ----------------------- */
+/* out bf16 [B*nq, H*HD] = softmax(q k^T * scale) v per (clip, head, query): CrossAttention.forward's SDPA
+ * (src/models/utils/modules.py:138-153) for the nq learned query tokens of AttentivePooler
+ * (src/models/attentive_pooler.py:96-102).  q bf16 [B*nq, H*HD]; kv bf16 [B*S, 2*H*HD] = the kv Linear's output
+ * (k | v halves, head-major).  HD in {32, 64, 80, 128}. */
+int vj_cross_attn_fwd(const void* q, const void* kv, void* out, int B, int nq, int S, int H, int HD, float scale,
+                      void* stream);
+
 /* ---- flat-buffer parameter kernels ------------------------------------------------------------ */
 /* dst bf16[n] = src fp32[n]: the per-step bf16 shadow of the fp32 master weights (what autocast's
  * weight cast does for every F.linear under torch.cuda.amp.autocast, app/vjepa/train.py:453). */

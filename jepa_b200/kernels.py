@@ -208,6 +208,13 @@ def token_std_bwd(z, pstd_total, grad_scale, scale, dz, weight, eps=1e-4):
     return dz
 
 
+def cross_attn_fwd(q, kv, out, B, nq, S, H, hd, scale):
+    """softmax(q k^T scale) v for nq query tokens per clip over S keys (attentive probe, modules.py:138-153)."""
+    _chk(q, BF16, "q"); _chk(kv, BF16, "kv"); _chk(out, BF16, "out")
+    _lib.call("vj_cross_attn_fwd", _p(q), _p(kv), _p(out), B, nq, S, H, hd, float(scale), _s())
+    return out
+
+
 def token_std_accum(z, pstd, weight, eps=1e-4):
     _chk(z, BF16, "z"); _chk(pstd, F32, "pstd")
     B, K, D = z.shape

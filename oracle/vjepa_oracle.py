@@ -236,3 +236,38 @@ def video_transform(buffer_u8, box, flip, crop_size, mean=(0.485, 0.456, 0.406),
     m = torch.tensor(mean, dtype=torch.float32) * 255.
     s = torch.tensor(std, dtype=torch.float32) * 255.
     return (out - m[:, None, None, None]) / s[:, None, None, None]
+
+
+# ---------------------------------------------------------------------------------------------
+# attentive probe of the frozen-encoder evaluations
+# ---------------------------------------------------------------------------------------------
+def cross_attention(S, pre, q, x, heads):
+    """CrossAttention.forward (src/models/utils/modules.py:138-153): q/kv projections, softmax(q k^T hd^-0.5) v per head.
+    NOTE the reference never applies `proj` in this forward (modules.py:152-153) - neither does this restatement."""
+    B, n, C = q.shape
+    hd = C // heads
+    qh = linear(q, S[pre + "q.weight"], S[pre + "q.bias"]).reshape(B, n, heads, hd).permute(0, 2, 1, 3)
+    N = x.shape[1]
+    kv = linear(x, S[pre + "kv.weight"], S[pre + "kv.bias"]).reshape(B, N, 2, heads, hd).permute(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]
+    att = torch.softmax((qh @ k.transpose(-2, -1)) * hd ** -0.5, dim=-1)
+    return (att @ v).transpose(1, 2).reshape(B, n, C)
+
+
+def attentive_pooler(S, x, heads, complete_block=True, pre="pooler."):
+    """AttentivePooler.forward (src/models/attentive_pooler.py:96-102), depth = 1; CrossAttentionBlock.forward
+    (modules.py:178-182): q = q + xattn(q, norm1(x)); q = q + mlp(norm2(q)); nn.LayerNorm default eps 1e-5."""
+    q = S[pre + "query_tokens"].repeat(len(x), 1, 1)
+    b = pre + "cross_attention_block."
+    if not complete_block:
+        return cross_attention(S, b, q, x, heads)
+    y = cross_attention(S, b + "xattn.", q, layer_norm(x, S[b + "norm1.weight"], S[b + "norm1.bias"], 1e-5), heads)
+    q = q + y
+    h = gelu(linear(layer_norm(q, S[b + "norm2.weight"], S[b + "norm2.bias"], 1e-5), S[b + "mlp.fc1.weight"],
+                    S[b + "mlp.fc1.bias"]))
+    return q + linear(h, S[b + "mlp.fc2.weight"], S[b + "mlp.fc2.bias"])
+
+
+def attentive_classifier(S, x, heads, complete_block=True):
+    """AttentiveClassifier.forward (attentive_pooler.py:133-136)."""
+    return linear(attentive_pooler(S, x, heads, complete_block).squeeze(1), S["linear.weight"], S["linear.bias"])

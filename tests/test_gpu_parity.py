@@ -683,6 +683,46 @@ def test_flat_grad_statistics_scaler_clip_and_loggers(dev):
     assert torch.equal(ks.flat, ref) and ks._shadow_fresh and torch.equal(ks.shadow, ref.to(torch.bfloat16))
 
 
+def test_attentive_probe_vs_reference_fixture(dev):
+    """jepa_b200.pooler.AttentiveClassifier (vj_cross_attn_fwd + LayerNorm + tcgen05 GEMMs) vs the outputs the
+    UNMODIFIED reference modules produced for the same seeded weights and inputs (tests/golden/make_golden_pooler.py);
+    head dims 64 / 32 / 80 / 128, complete_block on and off, class counts that are not multiples of 64."""
+    from test_oracle_cpu import _build_probe, _pooler_fixture
+    for case in _pooler_fixture()["cases"]:
+        clf = _build_probe(case).to(dev)
+        x = case["x"].to(dev, torch.bfloat16)
+        with torch.no_grad():
+            pooled = clf.pooler(x).float().cpu()
+            logits = clf(x).float().cpu()
+        assert pooled.shape == case["pooled"].shape and logits.shape == case["logits"].shape
+        assert rel_l2(pooled, case["pooled"]) < TOL_ACT and rel_l2(logits, case["logits"]) < TOL_ACT, case["cfg"]
+        with pytest.raises(NotImplementedError):      # inference-only: the probe is trained by the reference's eval loop
+            clf.pooler(x.float().requires_grad_(True))
+
+
+@pytest.mark.parametrize("D,H,S,B", [(1024, 16, 1568, 4), (1280, 16, 392, 3), (1280, 16, 4608, 1)])
+def test_attentive_probe_encoder_sizes_vs_oracle(dev, D, H, S, B):
+    """The probe at the encoders' real widths (ViT-L hd 64, ViT-H hd 80) and token counts (1568; C5's 4608) vs the oracle."""
+    from jepa_b200.pooler import AttentiveClassifier
+    from oracle import vjepa_oracle as O
+    torch.manual_seed(D + S)
+    clf = AttentiveClassifier(embed_dim=D, num_heads=H, depth=1, num_classes=400).eval()
+    with torch.no_grad():
+        for n, p in clf.named_parameters():
+            if n.endswith("bias") or "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+        # sharpen the attention a little (the init scale 0.02 gives an almost uniform softmax over S keys)
+        clf.pooler.query_tokens.mul_(20.0)
+        clf.pooler.cross_attention_block.xattn.q.weight.mul_(6.0)
+        clf.pooler.cross_attention_block.xattn.kv.weight.mul_(6.0)
+    x = bf(torch.randn(B, S, D, generator=torch.Generator().manual_seed(S)))
+    S_ = {k: v.double() for k, v in clf.state_dict().items()}
+    ref = O.attentive_classifier(S_, x.double(), H).float()
+    with torch.no_grad():
+        got = clf.to(dev)(x.to(dev, torch.bfloat16)).float().cpu()
+    assert rel_l2(got, ref) < TOL_ACT
+
+
 def test_out_layers_feature_taps_vs_oracle(dev):
     """f4 (frozen-encoder inference for the evals): VisionTransformer(out_layers=[...]) returns norm(x) after the chosen
     blocks (vision_transformer.py:183-190), here against the oracle."""

@@ -1,11 +1,14 @@
 """Pin the oracle: its fp32 C1 step must reproduce what the UNMODIFIED reference produced on the same
 seeded weights / clips / masks (tests/golden/golden_step_c1.pt, written by tests/golden/make_golden.py)."""
 import os
+import sys
 
 import pytest
 import torch
 
 from parity_util import run_c1_step_oracle, rel_l2
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.fixture(scope="module")
@@ -87,3 +90,65 @@ def test_input_pipeline_decisions_and_pixels_match_reference(golden_dir):
         y = O.video_transform(buf, ticket.box, ticket.flip, c["crop"])
         assert y.shape == c["out"].shape
         assert float((y - c["out"]).abs().max()) < 2e-5, c["seed"]
+
+
+# ------------------------------------------------------------------------------------------------ attentive probe (f4)
+def _pooler_fixture():
+    return torch.load(os.path.join(GOLDEN, "golden_pooler.pt"), weights_only=False)
+
+
+def _build_probe(case):
+    """jepa_b200.pooler.AttentiveClassifier built exactly like the fixture's reference module (same seed, same perturbation)."""
+    from jepa_b200.pooler import AttentiveClassifier
+    torch.manual_seed(case["seed"])
+    clf = AttentiveClassifier(depth=1, **case["cfg"]).eval()
+    with torch.no_grad():
+        for n, p in clf.named_parameters():
+            if n.endswith("bias") or "norm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    return clf
+
+
+def test_attentive_probe_state_dict_and_init_match_reference():
+    """Same keys, same order, and - draw for draw - the same initial values as src/models/attentive_pooler.py."""
+    sys.path.insert(0, os.path.join(GOLDEN))
+    from common import sha16
+    for case in _pooler_fixture()["cases"]:
+        sd = _build_probe(case).state_dict()
+        assert list(sd.keys()) == case["keys"]
+        for k, v in sd.items():
+            assert sha16(v) == case["sha"][k], k
+
+
+def test_oracle_attentive_probe_matches_reference_fixture():
+    from oracle import vjepa_oracle as O
+    for case in _pooler_fixture()["cases"]:
+        S = {k: v.double() for k, v in _build_probe(case).state_dict().items()}
+        cfg = case["cfg"]
+        pooled = O.attentive_pooler(S, case["x"].double(), cfg["num_heads"], cfg["complete_block"])
+        logits = O.attentive_classifier(S, case["x"].double(), cfg["num_heads"], cfg["complete_block"])
+        assert float((pooled.float() - case["pooled"]).abs().max()) < 2e-5
+        assert float((logits.float() - case["logits"]).abs().max()) < 2e-5
+
+
+def test_clip_aggregation_matches_reference_fixture():
+    """evals/video_classification_frozen/utils.py:86-159 regrouping (pure tensor plumbing, runs on CPU tensors)."""
+    from jepa_b200.pooler import ClipAggregation
+    fx = _pooler_fixture()["clipagg"]
+
+    class _Enc(torch.nn.Module):
+        embed_dim, num_heads = 16, 2
+
+        def forward(self, x):
+            B, C, T, H, W = x.shape
+            t = x.reshape(B, C, T // 2, 2, H // 4, 4, W // 4, 4).mean(dim=(3, 5, 7)).flatten(2).transpose(1, 2)
+            return torch.cat([t * (i + 1) for i in range(6)], dim=-1)[..., :16]
+
+    with torch.no_grad():
+        out = ClipAggregation(_Enc(), tubelet_size=2, max_frames=64, use_pos_embed=True, attend_across_segments=True)(
+            fx["xs1"], clip_indices=fx["idx"])
+        out2 = ClipAggregation(_Enc(), tubelet_size=2, attend_across_segments=False)(fx["xs2"])
+        out3 = ClipAggregation(_Enc(), tubelet_size=2, attend_across_segments=True)(fx["xs2"])
+    assert all(torch.allclose(a, b, atol=1e-6) for a, b in zip(out, fx["out"]))
+    assert all(torch.allclose(a, b, atol=1e-6) for va, vb in zip(out2, fx["out_noattend"]) for a, b in zip(va, vb))
+    assert all(torch.allclose(a, b, atol=1e-6) for a, b in zip(out3, fx["out_attend_nopos"]))
