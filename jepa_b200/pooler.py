@@ -197,47 +197,44 @@ class AttentiveClassifier(nn.Module):
 
 
 class ClipAggregation(nn.Module):
-    """evals/video_classification_frozen/utils.py:86-159: run every clip / view through the (frozen) encoder in ONE batch
-    and regroup the token sets; with attend_across_segments the temporal segments of a view are concatenated (and given the
-    1-D sin-cos position of their frames) so that the probe attends across them."""
+    """Frozen-encoder feature extraction for multi-clip / multi-view evaluation
+    (evals/video_classification_frozen/utils.py:86-159): every clip and view goes through the encoder in ONE batch, the
+    token sets come back grouped per view, and - with attend_across_segments - the temporal segments of a view are strung
+    together (optionally tagged with the 1-D sin-cos position of their frames) so that the probe attends across them."""
 
     def __init__(self, model, tubelet_size=2, max_frames=10000, use_pos_embed=False, attend_across_segments=False):
         super().__init__()
         self.model = model
         self.tubelet_size = tubelet_size
-        self.embed_dim = embed_dim = model.embed_dim
+        self.embed_dim = model.embed_dim
         self.num_heads = model.num_heads
         self.attend_across_segments = attend_across_segments
         self.pos_embed = None
         if use_pos_embed:
-            max_T = max_frames // tubelet_size
-            self.pos_embed = nn.Parameter(torch.zeros(1, max_T, embed_dim), requires_grad=False)
-            sincos = get_1d_sincos_pos_embed(embed_dim, max_T)
-            self.pos_embed.copy_(torch.from_numpy(sincos).float().unsqueeze(0))
+            steps = max_frames // tubelet_size
+            table = torch.from_numpy(get_1d_sincos_pos_embed(self.embed_dim, steps)).float()
+            self.pos_embed = nn.Parameter(table.unsqueeze(0), requires_grad=False)
 
     def forward(self, x, clip_indices=None):
-        num_clips = len(x)
-        num_views_per_clip = len(x[0])
-        B, C, T, H, W = x[0][0].size()
-        x = torch.cat([torch.cat(xi, dim=0) for xi in x], dim=0)
-        outputs = self.model(x)
-        _, N, D = outputs.size()
-        T = T // self.tubelet_size
-        N = N // T
-        eff_B = B * num_views_per_clip
-        all_outputs = [[] for _ in range(num_views_per_clip)]
-        for i in range(num_clips):
-            o = outputs[i * eff_B:(i + 1) * eff_B]
-            for j in range(num_views_per_clip):
-                all_outputs[j].append(o[j * B:(j + 1) * B])
+        """x: list (clips) of lists (views) of [B, C, T, H, W]; returns per view either the list of per-clip token sets
+        [B, N, D] or (attend_across_segments) one [B, clips*N, D] tensor."""
+        n_clips, n_views = len(x), len(x[0])
+        B, frames = x[0][0].shape[0], x[0][0].shape[2]
+        tokens = self.model(torch.cat([view for clip in x for view in clip], dim=0))      # clip-major, view-minor batch order
+        D = tokens.shape[-1]
+        t_tok = frames // self.tubelet_size                 # temporal tokens of one clip
+        s_tok = tokens.shape[1] // t_tok                    # spatial tokens per temporal step
+        per_view = [[tokens[(c * n_views + v) * B:(c * n_views + v + 1) * B] for c in range(n_clips)] for v in range(n_views)]
         if not self.attend_across_segments:
-            return all_outputs
-        for i, outs in enumerate(all_outputs):
-            outs = torch.cat([o.reshape(B, T, N, D) for o in outs], dim=1).flatten(1, 2)
-            if (self.pos_embed is not None) and (clip_indices is not None):
-                clip_indices = [c[:, ::self.tubelet_size] for c in clip_indices]
-                pos_embed = apply_masks(self.pos_embed.repeat(B, 1, 1), clip_indices, concat=False)
-                pos_embed = torch.cat(pos_embed, dim=1).unsqueeze(2).repeat(1, 1, N, 1).flatten(1, 2)
-                outs = outs + pos_embed.to(outs.dtype)
-            all_outputs[i] = outs
-        return all_outputs
+            return per_view
+        tags = None
+        if self.pos_embed is not None and clip_indices is not None:
+            # temporal position of every tubelet of every clip (frame index / tubelet_size picks a row of the sin-cos table)
+            steps = [idx[:, ::self.tubelet_size] for idx in clip_indices]
+            rows = apply_masks(self.pos_embed.expand(B, -1, -1), steps, concat=False)       # list of [B, t_tok, D]
+            tags = torch.cat(rows, dim=1).unsqueeze(2).expand(-1, -1, s_tok, -1).flatten(1, 2)
+        merged = []
+        for clips in per_view:
+            seq = torch.cat([c.reshape(B, t_tok, s_tok, D) for c in clips], dim=1).flatten(1, 2)
+            merged.append(seq if tags is None else seq + tags.to(seq.dtype))
+        return merged
